@@ -1,0 +1,199 @@
+/* hnsw_b200.h — C ABI of libhnsw_b200.so, the B200 (sm_100a) HNSW build + k-NN search engine
+ * that sits behind the OCaml API of lehy/ocaml-hnsw.
+ *
+ * The reference has no FFI seam of its own on this path (its only native boundary is the
+ * per-distance Lacaml stub, lib/ohnsw.ml:899).  The seam is therefore the set of OCaml values
+ * the benchmark and tests call; each entry point below names the reference interface it
+ * replaces.  The OCaml `external` declarations and C stubs a maintainer adds are in
+ * ocaml-hnsw_b200/ocaml/ and shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Vectors are fp32, row-major `float[n][dim]`, dense.  This is byte-for-byte the payload
+ *     of a `Lacaml.S.mat` of dim1 = dim, dim2 = n (Fortran layout, one vector per column;
+ *     lib/ohnsw.ml:840-846), so `Caml_ba_data_val` can be passed without a copy.
+ *   - Node ids are 0-based int32 (path B, lib/ohnsw.ml:842).  `id_base` on import/export lets
+ *     path A's 1-based graphs (lib/hnsw.ml:313-325) cross the boundary.
+ *   - Result buffers are caller-allocated `[nq][k]` (= a Lacaml k x nq mat).  Missing results
+ *     are padded with id -1 and distance NaN (lib/ohnsw.ml:879-881), or +inf when
+ *     HNSWB200_FLAVOUR_HNSW_BA is selected (lib/hnsw.ml:770-771).
+ *   - Every function returns a status; 0 is success.  The message for the last failure on the
+ *     calling thread is hnswb200_last_error().  Status -> OCaml exception:
+ *       1 -> Invalid_argument msg   (lib/ohnsw.ml:862 "knn: empty hgraph", :343, dataset.ml:112)
+ *       2 -> Failure msg            (CUDA / NCCL error)
+ *       3 -> Out_of_memory
+ *   - Host pointers unless the name ends in `_device`.  Input buffers are borrowed for the
+ *     duration of the call only.  Calls on one handle are serialised internally; the OCaml
+ *     stubs release the runtime lock around them.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with 2.
+ */
+#ifndef HNSW_B200_H
+#define HNSW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HNSWB200_OK 0
+#define HNSWB200_EINVAL 1
+#define HNSWB200_ECUDA 2
+#define HNSWB200_ENOMEM 3
+
+/* distance: the reference's `'a distance` closure (lib/ohnsw.ml:3) narrowed to a tag — an
+ * arbitrary OCaml closure cannot run on the GPU.  L2 is Ohnsw.distance_l2 (lib/ohnsw.ml:899,
+ * true Euclidean: sqrt of the fp32 sum of squares).  ANGULAR is 1 - a.b, IP is -a.b. */
+#define HNSWB200_L2 0
+#define HNSWB200_ANGULAR 1
+#define HNSWB200_IP 2
+
+/* search mode.  PARITY reproduces the reference's sequential best-first search id for id
+ * (one expansion per iteration, exact visited set, (distance,id) tie order).  FAST may
+ * expand speculatively; same result contract (k nearest found, ascending) but not id parity. */
+#define HNSWB200_MODE_PARITY 0
+#define HNSWB200_MODE_FAST 1
+
+/* which reference code path's quirks are mirrored:
+ * OHNSW   = lib/ohnsw.ml   (strict accept `d < top`, 2M links for a new node on layer 0,
+ *                           -1/NaN padding)
+ * HNSW_BA = lib/hnsw.ml + lib/hnsw_algo.ml `Hnsw.Ba` (ties accepted `d <= top`,
+ *                           M links for a new node on every layer, +inf padding) */
+#define HNSWB200_FLAVOUR_OHNSW 0
+#define HNSWB200_FLAVOUR_HNSW_BA 1
+
+typedef struct hnswb200_index hnswb200_index;
+
+typedef struct hnswb200_info {
+  int64_t n;            /* number of nodes                      Hgraph.num_nodes  ohnsw.ml:335 */
+  int32_t dim;
+  int32_t metric;
+  int32_t M;            /* num_connections                      ohnsw.ml:767 */
+  int32_t ef_construction; /* num_nodes_search_construction     ohnsw.ml:768 */
+  int32_t max_layer;    /* Hgraph.max_layer                     ohnsw.ml:346 */
+  int64_t entry_point;  /* -1 when empty                        ohnsw.ml:340 */
+  int32_t slots0;       /* adjacency row width on layer 0 (2M)  ohnsw.ml:818 */
+  int32_t slots_upper;  /* row width on layers >= 1 (M) */
+  int32_t flavour;
+  int32_t device;
+} hnswb200_info;
+
+/* Work counters of the last search call and the last build call, plus graph shape.
+ * n_dist counts what the reference's distance-call counter counts (lib/hnsw.ml:732-751). */
+typedef struct hnswb200_stats {
+  uint64_t search_queries;
+  uint64_t search_n_dist;     /* distance evaluations */
+  uint64_t search_n_exp0;     /* adjacency rows read on layer 0 */
+  uint64_t search_n_expU;     /* adjacency rows read on layers >= 1 */
+  uint64_t search_visited_overflows; /* queries whose visited set left shared memory */
+  double   search_algorithmic_bytes; /* n_dist*4*dim + n_exp0*4*slots0 + n_expU*4*slots_upper + nq*(4*dim + 8*k) */
+  double   search_kernel_ms;  /* device time of the search kernel (CUDA events) */
+  uint64_t build_inserts;
+  uint64_t build_n_dist;
+  uint64_t build_n_exp;
+  double   build_algorithmic_bytes;
+  double   build_seconds;     /* wall time of the last build/insert call, H2D included */
+  uint64_t gpu_launches;      /* kernels launched by this handle since creation */
+  /* Hgraph.Stats (lib/hnsw.ml:353-375): per layer size / min / max / mean degree / isolated */
+  int32_t  num_layers;
+  int64_t  layer_nodes[16];
+  int32_t  layer_min_degree[16];
+  int32_t  layer_max_degree[16];
+  double   layer_mean_degree[16];
+  int64_t  layer_isolated[16];
+} hnswb200_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Replaces Ohnsw.Hgraph.create (lib/ohnsw.ml:316-324) / Hnsw.Ba's Hgraph.create
+ * (lib/hnsw.ml:388-394).  `seed` drives the level draw (lib/ohnsw.ml:781) when levels are not
+ * supplied.  `device` is the CUDA ordinal this index lives on (one process per GPU). */
+int hnswb200_create(hnswb200_index** out, int dim, int metric, int M, int ef_construction,
+                    uint64_t seed, int device);
+int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
+/* Tunables: "hash_slots" (visited hash size per query, power of two; 0 = derive from ef),
+ * "build_batch" (max inserts per GPU batch), "warps_per_cta". */
+int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
+int hnswb200_destroy(hnswb200_index* idx);
+
+/* ---- build --------------------------------------------------------------------------------- */
+
+/* Replaces Ohnsw.build_batch_bigarray (lib/ohnsw.ml:840-857) and Hnsw.Ba.build
+ * (lib/hnsw.ml:753-761): index `n` vectors in row order.  `levels` (int32[n], may be NULL) are
+ * the per-node levels the reference would have drawn (lib/ohnsw.ml:781) — supply them to
+ * compare against a reference/oracle build on identical levels. */
+int hnswb200_build(hnswb200_index* idx, const float* data, int64_t n, const int32_t* levels);
+
+/* Replaces repeated Ohnsw.insert (lib/ohnsw.ml:766-837) / Hnsw_algo.BuildIncr.insert
+ * (lib/hnsw_algo.ml:901): append `n` more vectors to an existing index. */
+int hnswb200_insert(hnswb200_index* idx, const float* data, int64_t n, const int32_t* levels);
+
+/* ---- query --------------------------------------------------------------------------------- */
+
+/* Replaces Ohnsw.knn_batch_bigarray (lib/ohnsw.ml:877-897) and Hnsw.Ba.knn_batch
+ * (lib/hnsw.ml:769-777); with nq = 1, Ohnsw.knn (lib/ohnsw.ml:859-875) / Hnsw.Ba.knn.
+ * `ef` is the beam width: the reference's path B has no separate ef (search_k is called with
+ * k, lib/ohnsw.ml:873), so pass ef = k for the literal behaviour, or ef > k for "search with
+ * ~k:ef, keep the first k rows".  ids may be NULL (Hnsw.Ba.knn_batch returns distances only).
+ * Fails with EINVAL "knn: empty hgraph" on an empty index (lib/ohnsw.ml:862). */
+int hnswb200_search(hnswb200_index* idx, const float* queries, int64_t nq, int k, int ef, int mode,
+                    int32_t* ids, float* dists);
+
+/* Same, all buffers already in this index's device memory: queries `float[nq][dim]` dense,
+ * outputs `[nq][k]`.  `stream` is a cudaStream_t (NULL = the index's own stream; the call then
+ * synchronises before returning, otherwise it only enqueues). */
+int hnswb200_search_device(hnswb200_index* idx, const float* d_queries, int64_t nq, int k, int ef,
+                           int mode, int32_t* d_ids, float* d_dists, void* stream);
+
+/* Per-query work counters of the last search call: uint32[nq][3] = n_dist, n_exp0, n_expU. */
+int hnswb200_last_search_counters(hnswb200_index* idx, uint32_t* out, int64_t nq);
+
+/* ---- graph exchange (the parity vehicle) ------------------------------------ */
+
+/* Load a graph built elsewhere (the reference through an exporter functor over
+ * Hnsw_algo.KNN_HGRAPH / a walker over Ohnsw.Hgraph.t, or the oracle): per layer l in
+ * 0..max_layer a CSR (`layer_offsets[l]` int64[n+1], `layer_nbrs[l]` int32[nnz_l]) whose rows
+ * keep the reference's list order (head first, lib/ohnsw.ml:116-124).  Ids in the CSR and
+ * `entry` are offset by `id_base` (0 for Ohnsw, 1 for Hnsw.Ba). */
+int hnswb200_import_graph(hnswb200_index* idx, const float* data, int64_t n, int id_base,
+                          int max_layer, int64_t entry, const int64_t* const* layer_offsets,
+                          const int32_t* const* layer_nbrs);
+
+/* Two-call pattern: with nbrs == NULL only *nnz is written.  offsets is int64[n+1]. */
+int hnswb200_export_layer(hnswb200_index* idx, int layer, int id_base, int64_t* offsets,
+                          int32_t* nbrs, int64_t* nnz);
+/* int32[n]: highest layer each node has adjacency rows on. */
+int hnswb200_export_levels(hnswb200_index* idx, int32_t* levels);
+
+/* ---- evaluation helpers (benchmark/dataset.ml) ----------------------------------------------- */
+
+/* Replaces brute_force_knn_l2 (benchmark/dataset.ml:15-30): exact k nearest of every query,
+ * ascending by (distance, id); the reference returns distances only, ids are extra. */
+int hnswb200_bruteforce_knn(const float* data, int64_t n, const float* queries, int64_t nq, int dim,
+                            int k, int metric, int device, int32_t* ids, float* dists);
+
+/* Replaces Recall.compute (benchmark/dataset.ml:105-127) on `[nq][k]` arrays. */
+int hnswb200_recall(const float* expected, const float* got, int64_t nq, int k, double epsilon,
+                    double* out);
+
+/* ---- multi-GPU: per-shard top-k merge ------------------------------------------ */
+
+/* After an all-gather of per-shard results: d_ids/d_dists are `[n_shards][nq][k]` in device
+ * memory (ids already global), merged into the k best per query `[nq][k]`, ascending by
+ * (distance, id), -1/NaN padded. */
+int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n_shards, int64_t nq,
+                               int k, int32_t* d_out_ids, float* d_out_dists, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+
+int hnswb200_get_info(hnswb200_index* idx, hnswb200_info* out);
+int hnswb200_get_stats(hnswb200_index* idx, hnswb200_stats* out);
+/* Pin / unpin a caller buffer (a Bigarray payload) so H2D/D2H copies are asynchronous DMA. */
+int hnswb200_host_register(const void* ptr, int64_t bytes);
+int hnswb200_host_unregister(const void* ptr);
+const char* hnswb200_last_error(void);
+const char* hnswb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNSW_B200_H */

@@ -1,0 +1,220 @@
+// Device-side building blocks shared by the search and build kernels (sm_100a).
+//
+// Data layout in HBM (one index = one GPU):
+//   vec   : float[cap][ld]      ld = dim rounded up to 4 floats, zero padded; one 16-byte
+//                               aligned row per node -> every gather is 128-bit loads
+//   adj0  : int32[cap][slots0]  layer-0 adjacency, fixed width (2M), list order kept
+//                               (slot 0 = list head, lib/ohnsw.ml:116), -1 terminated
+//   upper_off : int32[cap]      first upper-layer row of the node, -1 if level 0
+//   adjU  : int32[rowsU][slotsU] rows of layers >= 1: node i, layer l -> row upper_off[i]+l-1
+//   level : int8[cap]
+//
+// Distances are evaluated by a TEAM of 8 lanes per vector, one float4 per lane per step, with
+// a fixed summation order (see oracle/ohnsw_oracle.hpp, SUM_TEAM8): lane t accumulates chunks
+// t, t+8, ... in index order with fused multiply-add, then a butterfly over lane^4, ^2, ^1.
+// A warp evaluates four vectors per load instruction, each team reading one whole 128-byte
+// line per step.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TEAM = 8;
+constexpr int TIES_CAP = 32;
+constexpr uint64_t KEY_INF = ~0ull;
+
+struct GraphView {
+  const float* vec;
+  const int32_t* adj0;
+  const int32_t* upper_off;
+  const int32_t* adjU;
+  int ld4;        // float4 per vector row
+  int chunks;     // float4 chunks that carry data ( = ld4 )
+  int slots0;
+  int slotsU;
+  int max_layer;
+  int entry;
+  int n;
+  int metric;     // 0 L2, 1 angular, 2 ip
+};
+
+// ---- keys: (distance, id) total order in one u64; bit 0 = "expanded" ---------------------------
+__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
+  f = f + 0.0f;                                   // -0 -> +0: equal distances get equal bits
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
+  return ((uint64_t)f2ord(d) << 32) | ((uint64_t)id << 1);
+}
+__host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return (uint32_t)(k >> 1) & 0x7fffffffu; }
+__host__ __device__ __forceinline__ float key_dist(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
+
+// ---- distance ------------------------------------------------------------------------------------
+__device__ __forceinline__ float acc4(float acc, const float4& a, const float4& b, bool dot) {
+  if (dot) {
+    acc = __fmaf_rn(a.x, b.x, acc); acc = __fmaf_rn(a.y, b.y, acc);
+    acc = __fmaf_rn(a.z, b.z, acc); acc = __fmaf_rn(a.w, b.w, acc);
+  } else {
+    float x = __fsub_rn(a.x, b.x); acc = __fmaf_rn(x, x, acc);
+    x = __fsub_rn(a.y, b.y); acc = __fmaf_rn(x, x, acc);
+    x = __fsub_rn(a.z, b.z); acc = __fmaf_rn(x, x, acc);
+    x = __fsub_rn(a.w, b.w); acc = __fmaf_rn(x, x, acc);
+  }
+  return acc;
+}
+__device__ __forceinline__ float team_reduce(float acc) {
+  acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
+  acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
+  acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
+  return acc;
+}
+__device__ __forceinline__ float finish_metric(float acc, int metric) {
+  return metric == 0 ? acc : (metric == 1 ? __fsub_rn(1.0f, acc) : -acc);
+}
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Distances from the target (register copy q[CPL] when CPL > 0, shared copy qs otherwise) to
+// two nodes per team (8 vectors per warp), all loads issued before the first use.
+// node < 0 = no work for this team.  All 32 lanes must call.
+template <int CPL>
+__device__ __forceinline__ void team_dist2(const GraphView& g, const float4* q, const float4* qs, int node0,
+                                           int node1, int tl, float& out0, float& out1) {
+  const bool dot = g.metric != 0;
+  float a0 = 0.f, a1 = 0.f;
+  const float4* r0 = reinterpret_cast<const float4*>(g.vec) + (size_t)(node0 < 0 ? 0 : node0) * g.ld4;
+  const float4* r1 = reinterpret_cast<const float4*>(g.vec) + (size_t)(node1 < 0 ? 0 : node1) * g.ld4;
+  if (CPL > 0) {
+    float4 v0[CPL > 0 ? CPL : 1], v1[CPL > 0 ? CPL : 1];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      int ch = tl + TEAM * c;
+      bool in = ch < g.chunks;
+      v0[c] = (in && node0 >= 0) ? ldg4(r0 + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v1[c] = (in && node1 >= 0) ? ldg4(r1 + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+      if (tl + TEAM * c < g.chunks) {      // padding chunks add nothing (keeps -0/+0 exact too)
+        a0 = acc4(a0, q[c], v0[c], dot);
+        a1 = acc4(a1, q[c], v1[c], dot);
+      }
+    }
+  } else {
+    for (int ch = tl; ch < g.chunks; ch += 4 * TEAM) {
+      float4 v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int c = ch + u * TEAM;
+        bool in = c < g.chunks;
+        v0[u] = (in && node0 >= 0) ? ldg4(r0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v1[u] = (in && node1 >= 0) ? ldg4(r1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int c = ch + u * TEAM;
+        if (c < g.chunks) {
+          float4 qq = qs[c];
+          a0 = acc4(a0, qq, v0[u], dot);
+          a1 = acc4(a1, qq, v1[u], dot);
+        }
+      }
+    }
+  }
+  out0 = finish_metric(team_reduce(a0), g.metric);
+  out1 = finish_metric(team_reduce(a1), g.metric);
+}
+
+// ids[0..cnt) (shared) -> d[0..cnt) (shared).  cnt is warp-uniform.
+template <int CPL>
+__device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, const float4* qs,
+                                           const uint32_t* ids, float* d, int cnt, int lane) {
+  const int tl = lane & (TEAM - 1), team = lane >> 3;
+  for (int base = 0; base < cnt; base += 8) {
+    int j0 = base + team, j1 = base + 4 + team;
+    int n0 = j0 < cnt ? (int)ids[j0] : -1;
+    int n1 = j1 < cnt ? (int)ids[j1] : -1;
+    float a0, a1;
+    team_dist2<CPL>(g, q, qs, n0, n1, tl, a0, a1);
+    if (tl == 0) {
+      if (n0 >= 0) d[j0] = a0;
+      if (n1 >= 0) d[j1] = a1;
+    }
+  }
+  __syncwarp();
+}
+
+// ---- exact visited set ---------------------------------------------------------------------------
+// Open-addressing hash of id+1 in shared memory; when it would exceed its load bound the set
+// moves to a bitset over all n nodes borrowed from a global pool (exactness is never traded).
+struct VisitedSet {
+  uint32_t* tab;        // shared, `mask+1` slots
+  uint32_t mask;
+  uint32_t shift;
+  uint32_t limit;       // max entries kept in shared memory
+  uint32_t count;       // warp-uniform
+  uint32_t* bits;       // non-null once spilled
+  int pool_slot;
+};
+__device__ __forceinline__ bool hash_test_and_set(uint32_t* tab, uint32_t mask, uint32_t shift, uint32_t id) {
+  uint32_t key = id + 1u;
+  uint32_t h = (id * 2654435761u) >> shift;
+  while (true) {
+    uint32_t old = atomicCAS(&tab[h], 0u, key);
+    if (old == 0u) return true;
+    if (old == key) return false;
+    h = (h + 1u) & mask;
+  }
+}
+__device__ __forceinline__ void visited_clear(VisitedSet& v, int lane) {
+  uint4* t4 = reinterpret_cast<uint4*>(v.tab);
+  for (uint32_t i = lane; i < (v.mask + 1u) / 4u; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  v.count = 0;
+  __syncwarp();
+}
+
+// ---- the beam: `near` as a sorted array of keys in shared memory --------------------------------
+// Insert K keeping ascending order; capacity ef (the largest key falls off when full).
+// Returns the key that fell off (0 if none).  fu = index below which everything is expanded.
+__device__ __forceinline__ uint64_t beam_insert(uint64_t* keys, int& n, int ef, uint64_t K, int lane, int& fu) {
+  uint64_t evicted = 0;
+  if (n == ef) {
+    evicted = keys[ef - 1];
+    if (K > evicted) return K;             // only reachable when ties are accepted (Hnsw.Ba flavour)
+  }
+  const int last = (n == ef) ? ef - 1 : n;
+  int p = last;
+  for (int base = last & ~31; base >= 0; base -= 32) {
+    int idx = base + lane;
+    uint64_t cur = idx < n ? keys[idx] : KEY_INF;
+    bool left_less = (idx == 0) || ((idx - 1 < n ? keys[idx - 1] : KEY_INF) < K);
+    uint64_t left = idx > 0 && idx - 1 < n ? keys[idx - 1] : KEY_INF;
+    bool keep = cur < K;
+    bool write = !keep && idx <= last;
+    __syncwarp();
+    if (write) keys[idx] = left_less ? K : left;
+    unsigned here = __ballot_sync(FULL, write && left_less);
+    if (here) p = base + __ffs(here) - 1;
+    __syncwarp();
+    if (__shfl_sync(FULL, (int)keep, 0)) break;
+  }
+  if (n < ef) n++;
+  if (p < fu) fu = p;
+  return evicted;
+}
+
+}  // namespace hb

@@ -1,0 +1,568 @@
+// libhnsw_b200.so — C ABI (include/hnsw_b200.h) over the sm_100a kernels.
+// Host logic only: device memory layout, graph import/export, kernel launches, counters.
+// There is no CPU compute path in this library; without a CUDA device every compute entry
+// point fails with HNSWB200_ECUDA.
+#include "../../include/hnsw_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "search.cuh"
+#include "build.cuh"
+#include "bruteforce.cuh"
+#include "merge.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct HbError : std::runtime_error {
+  int code;
+  HbError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] void fail(int code, const std::string& m) { throw HbError(code, m); }
+
+#define CUDA_CHECK(x)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) {                                                                       \
+      int code_ = e_ == cudaErrorMemoryAllocation ? HNSWB200_ENOMEM : HNSWB200_ECUDA;              \
+      fail(code_, std::string(#x) + ": " + cudaGetErrorString(e_));                                \
+    }                                                                                              \
+  } while (0)
+
+template <class F>
+int guard(F&& f) {
+  try { f(); return HNSWB200_OK; }
+  catch (const HbError& e) { g_err = e.what(); return e.code; }
+  catch (const std::bad_alloc&) { g_err = "out of memory"; return HNSWB200_ENOMEM; }
+  catch (const std::exception& e) { g_err = e.what(); return HNSWB200_ECUDA; }
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  // grow-only; contents are NOT preserved unless keep is set
+  void reserve(size_t want, bool keep = false, cudaStream_t s = 0) {
+    if (want <= n) return;
+    T* q = nullptr;
+    CUDA_CHECK(cudaMalloc(&q, want * sizeof(T)));
+    if (keep && p && n) CUDA_CHECK(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (keep && p) CUDA_CHECK(cudaStreamSynchronize(s));
+    if (p) cudaFree(p);
+    p = q; n = want;
+  }
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+struct hnswb200_index {
+  // configuration
+  int dim = 0, metric = 0, M = 0, efC = 0, device = 0, flavour = HNSWB200_FLAVOUR_OHNSW;
+  uint64_t seed = 0, rng_state = 0;
+  int64_t param_hash_slots = 0, param_build_batch = 0, param_warps_per_cta = 4;
+  // graph
+  int64_t n = 0, cap = 0;
+  int ld = 0, slots0 = 0, slotsU = 0, max_layer = 0;
+  int64_t entry = -1;
+  int64_t rowsU = 0, capU = 0;
+  DevBuf<float> vec;
+  DevBuf<int32_t> adj0, upper_off, adjU;
+  DevBuf<int8_t> level;
+  std::vector<int8_t> h_level;        // host mirror of level (bookkeeping for build / export)
+  std::vector<int32_t> h_upper_off;
+  // scratch
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<float> d_q, d_dists;
+  DevBuf<int32_t> d_ids;
+  DevBuf<uint32_t> d_counters, d_bitpool;
+  DevBuf<int> d_pool_busy;
+  DevBuf<unsigned int> d_next;
+  DevBuf<unsigned long long> d_events;
+  int pool_size = 0, pool_words = 0;
+  int num_sms = 0, max_smem_optin = 0;
+  // stats
+  hnswb200_stats st{};
+  int64_t last_nq = 0;
+  std::mutex mu;
+
+  hb::GraphView view() const {
+    hb::GraphView g;
+    g.vec = vec.p; g.adj0 = adj0.p; g.upper_off = upper_off.p; g.adjU = adjU.p;
+    g.ld4 = ld / 4; g.chunks = ld / 4; g.slots0 = slots0; g.slotsU = slotsU;
+    g.max_layer = max_layer; g.entry = (int)entry; g.n = (int)n; g.metric = metric;
+    return g;
+  }
+};
+
+namespace {
+
+void use_device(hnswb200_index* x) { CUDA_CHECK(cudaSetDevice(x->device)); }
+
+void init_device(hnswb200_index* x) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail(HNSWB200_ECUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  if (x->device < 0 || x->device >= count) fail(HNSWB200_EINVAL, "device ordinal out of range");
+  use_device(x);
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, x->device));
+  x->num_sms = prop.multiProcessorCount;
+  x->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreate(&x->ev0));
+  CUDA_CHECK(cudaEventCreate(&x->ev1));
+}
+
+// Copy host rows [n][dim] into device rows [n][ld] (zero padded).
+void upload_rows(float* dst, int ld, const float* src, int dim, int64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  if (ld == dim) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  } else {
+    CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)n * ld * sizeof(float), s));
+    CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)dim * sizeof(float),
+                                 (size_t)dim * sizeof(float), (size_t)n, cudaMemcpyHostToDevice, s));
+  }
+}
+
+// ---- search ---------------------------------------------------------------------------------------
+struct SearchPlan {
+  int cpl, warps, ef_cap, hash_slots, q_chunks, smem_per_warp, grid;
+  size_t smem;
+};
+
+SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
+  SearchPlan pl;
+  int chunks = x->ld / 4;
+  int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
+  pl.cpl = cpl <= 4 ? cpl : 0;                        // register-resident query up to 128 dims
+  pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
+  pl.ef_cap = round_up(ef, 32);
+  int hs = x->param_hash_slots > 0 ? next_pow2((int)x->param_hash_slots) : next_pow2(std::max(1024, 48 * ef));
+  hs = std::min(hs, 32768);
+  pl.hash_slots = hs;
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
+  if (pl.smem_per_warp > x->max_smem_optin) {
+    while (pl.hash_slots > 1024 && hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks) > x->max_smem_optin)
+      pl.hash_slots >>= 1;
+    pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
+    if (pl.smem_per_warp > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
+  }
+  int warps = (int)std::max<int64_t>(1, std::min<int64_t>(x->param_warps_per_cta, 8));
+  while (warps > 1 && (size_t)warps * pl.smem_per_warp > (size_t)x->max_smem_optin) warps--;
+  pl.warps = warps;
+  pl.smem = (size_t)warps * pl.smem_per_warp;
+  // persistent grid: as many CTAs as fit per SM (shared memory is the limiter), times the SM count
+  int per_sm = std::max(1, std::min(16, (int)((size_t)(228 * 1024 - 1024) / (pl.smem + 1024))));
+  per_sm = std::min(per_sm, std::max(1, 48 / warps));   // ~48 resident warps is plenty for the gather
+  int64_t need = (nq + warps - 1) / warps;
+  pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * per_sm, need));
+  return pl;
+}
+
+template <int CPL>
+void launch_search(const hb::SearchParams& p, const SearchPlan& pl, cudaStream_t s) {
+  CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  hb::search_kernel<CPL><<<pl.grid, pl.warps * 32, pl.smem, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void ensure_pool(hnswb200_index* x, int total_warps) {
+  int words = (int)((x->n + 31) / 32);
+  words = round_up(std::max(words, 1), 4);
+  // a spilled query borrows one n-bit set; cap the pool at 1 GiB
+  int64_t max_sets = std::max<int64_t>(1, (int64_t(1) << 30) / ((int64_t)words * 4));
+  int want = (int)std::min<int64_t>(total_warps, max_sets);
+  if (want > x->pool_size || words > x->pool_words) {
+    x->d_bitpool.release();
+    x->d_bitpool.reserve((size_t)want * words);
+    CUDA_CHECK(cudaMemsetAsync(x->d_bitpool.p, 0, (size_t)want * words * 4, x->stream));
+    x->d_pool_busy.reserve((size_t)want);
+    CUDA_CHECK(cudaMemsetAsync(x->d_pool_busy.p, 0, (size_t)x->d_pool_busy.n * sizeof(int), x->stream));
+    x->pool_size = want; x->pool_words = words;
+  }
+}
+
+void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
+                   int32_t* d_ids, float* d_dists, cudaStream_t s, bool own_stream) {
+  if (nq < 0 || k <= 0) fail(HNSWB200_EINVAL, "search: nq must be >= 0 and k > 0");
+  if (ef < k) fail(HNSWB200_EINVAL, "search: ef must be >= k");
+  if (mode != HNSWB200_MODE_PARITY && mode != HNSWB200_MODE_FAST) fail(HNSWB200_EINVAL, "search: unknown mode");
+  if (x->n == 0 || x->entry < 0) fail(HNSWB200_EINVAL, "knn: empty hgraph");     // lib/ohnsw.ml:862
+  if (ef > 4096) fail(HNSWB200_EINVAL, "search: ef > 4096 is not supported");
+  if (nq == 0) return;
+  SearchPlan pl = plan_search(x, ef, nq);
+  ensure_pool(x, pl.grid * pl.warps);
+  x->d_counters.reserve((size_t)nq * 3);
+  x->d_next.reserve(1);
+  x->d_events.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, sizeof(unsigned int), s));
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
+  hb::SearchParams p;
+  p.g = x->view();
+  p.queries = d_queries; p.nq = nq; p.ef = ef; p.k = k; p.ef_cap = pl.ef_cap;
+  p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
+  p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
+  p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp;
+  p.out_ids = d_ids; p.out_dists = d_dists; p.counters = x->d_counters.p;
+  p.next_query = x->d_next.p; p.bitset_pool = x->d_bitpool.p; p.pool_busy = x->d_pool_busy.p;
+  p.pool_size = x->pool_size; p.words = x->pool_words; p.events = x->d_events.p;
+  CUDA_CHECK(cudaEventRecord(x->ev0, s));
+  switch (pl.cpl) {
+    case 1: launch_search<1>(p, pl, s); break;
+    case 2: launch_search<2>(p, pl, s); break;
+    case 3: launch_search<3>(p, pl, s); break;
+    case 4: launch_search<4>(p, pl, s); break;
+    default: launch_search<0>(p, pl, s); break;
+  }
+  CUDA_CHECK(cudaEventRecord(x->ev1, s));
+  x->st.gpu_launches += 1;
+  x->last_nq = nq;
+  x->st.search_queries = (uint64_t)nq;
+  if (own_stream) {
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    unsigned long long evs[2];
+    CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
+    x->st.search_visited_overflows = evs[0];
+    if (evs[1] && mode == HNSWB200_MODE_PARITY)
+      fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
+                               std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
+  }
+}
+
+// ---- import / export ----------------------------------------------------------------------------------
+void allocate_graph(hnswb200_index* x, int64_t cap, int64_t capU, bool keep) {
+  use_device(x);
+  x->vec.reserve((size_t)cap * x->ld, keep, x->stream);
+  x->adj0.reserve((size_t)cap * x->slots0, keep, x->stream);
+  x->upper_off.reserve((size_t)cap, keep, x->stream);
+  x->level.reserve((size_t)cap, keep, x->stream);
+  x->adjU.reserve((size_t)std::max<int64_t>(capU, 1) * x->slotsU, keep, x->stream);
+  x->cap = cap; x->capU = std::max<int64_t>(capU, 1);
+}
+
+void import_graph(hnswb200_index* x, const float* data, int64_t n, int id_base, int max_layer, int64_t entry,
+                  const int64_t* const* offs, const int32_t* const* nbrs) {
+  if (n <= 0) fail(HNSWB200_EINVAL, "import_graph: n must be > 0");
+  if (n >= (int64_t(1) << 31) - 1) fail(HNSWB200_EINVAL, "import_graph: n too large");
+  if (max_layer < 0 || max_layer > 15) fail(HNSWB200_EINVAL, "import_graph: max_layer must be in 0..15");
+  entry -= id_base;
+  if (entry < 0 || entry >= n) fail(HNSWB200_EINVAL, "Hgraph.set_entry_point: invalid node");   // lib/ohnsw.ml:343
+  int maxdeg0 = 0, maxdegU = 0;
+  std::vector<int8_t> lvl((size_t)n, 0);
+  for (int l = 0; l <= max_layer; l++) {
+    const int64_t* o = offs[l];
+    if (o[0] != 0) fail(HNSWB200_EINVAL, "import_graph: offsets must start at 0");
+    for (int64_t i = 0; i < n; i++) {
+      int64_t deg = o[i + 1] - o[i];
+      if (deg < 0) fail(HNSWB200_EINVAL, "import_graph: offsets must be non-decreasing");
+      if (deg > 4096) fail(HNSWB200_EINVAL, "import_graph: degree > 4096");
+      if (l == 0) maxdeg0 = std::max<int>(maxdeg0, (int)deg);
+      else { maxdegU = std::max<int>(maxdegU, (int)deg); if (deg > 0) lvl[i] = (int8_t)l; }
+    }
+  }
+  lvl[(size_t)entry] = (int8_t)max_layer;
+  x->slots0 = std::max(2 * x->M, maxdeg0);
+  x->slotsU = std::max(x->M, maxdegU);
+  std::vector<int32_t> uoff((size_t)n, -1);
+  int64_t rows = 0;
+  for (int64_t i = 0; i < n; i++) if (lvl[i] > 0) { uoff[i] = (int32_t)rows; rows += lvl[i]; }
+  if (rows >= (int64_t(1) << 31)) fail(HNSWB200_EINVAL, "import_graph: too many upper-layer rows");
+  std::vector<int32_t> a0((size_t)n * x->slots0, -1), aU((size_t)std::max<int64_t>(rows, 1) * x->slotsU, -1);
+  std::vector<int32_t> seen;
+  for (int l = 0; l <= max_layer; l++) {
+    const int64_t* o = offs[l];
+    for (int64_t i = 0; i < n; i++) {
+      int64_t deg = o[i + 1] - o[i];
+      if (!deg) continue;
+      int32_t* row = l == 0 ? &a0[(size_t)i * x->slots0] : &aU[((size_t)uoff[i] + l - 1) * x->slotsU];
+      seen.assign(nbrs[l] + o[i], nbrs[l] + o[i + 1]);
+      for (int64_t j = 0; j < deg; j++) {
+        int64_t v = (int64_t)seen[j] - id_base;
+        if (v < 0 || v >= n) fail(HNSWB200_EINVAL, "import_graph: neighbour id out of range");
+        row[j] = (int32_t)v;
+      }
+      std::sort(seen.begin(), seen.end());
+      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end())
+        fail(HNSWB200_EINVAL, "import_graph: duplicate neighbour id in a row");
+    }
+  }
+  x->vec.release(); x->adj0.release(); x->upper_off.release(); x->level.release(); x->adjU.release();
+  allocate_graph(x, n, rows, false);
+  upload_rows(x->vec.p, x->ld, data, x->dim, n, x->stream);
+  CUDA_CHECK(cudaMemcpyAsync(x->adj0.p, a0.data(), a0.size() * 4, cudaMemcpyHostToDevice, x->stream));
+  CUDA_CHECK(cudaMemcpyAsync(x->adjU.p, aU.data(), aU.size() * 4, cudaMemcpyHostToDevice, x->stream));
+  CUDA_CHECK(cudaMemcpyAsync(x->upper_off.p, uoff.data(), uoff.size() * 4, cudaMemcpyHostToDevice, x->stream));
+  CUDA_CHECK(cudaMemcpyAsync(x->level.p, lvl.data(), lvl.size(), cudaMemcpyHostToDevice, x->stream));
+  CUDA_CHECK(cudaStreamSynchronize(x->stream));
+  x->n = n; x->rowsU = rows; x->max_layer = max_layer; x->entry = entry;
+  x->h_level = lvl; x->h_upper_off = uoff;
+}
+
+// host copy of one layer's rows: deg[i], and the row contents
+void download_layer(hnswb200_index* x, int layer, std::vector<int32_t>& rows, int& slots) {
+  use_device(x);
+  if (layer == 0) {
+    slots = x->slots0;
+    rows.resize((size_t)x->n * slots);
+    CUDA_CHECK(cudaMemcpy(rows.data(), x->adj0.p, rows.size() * 4, cudaMemcpyDeviceToHost));
+  } else {
+    slots = x->slotsU;
+    rows.resize((size_t)std::max<int64_t>(x->rowsU, 1) * slots);
+    CUDA_CHECK(cudaMemcpy(rows.data(), x->adjU.p, rows.size() * 4, cudaMemcpyDeviceToHost));
+  }
+}
+const int32_t* layer_row(hnswb200_index* x, int layer, const std::vector<int32_t>& rows, int slots, int64_t i) {
+  if (layer == 0) return &rows[(size_t)i * slots];
+  if (x->h_level[(size_t)i] < layer) return nullptr;
+  return &rows[((size_t)x->h_upper_off[(size_t)i] + layer - 1) * slots];
+}
+int row_degree(const int32_t* row, int slots) {
+  int d = 0;
+  while (row && d < slots && row[d] >= 0) d++;
+  return d;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* hnswb200_last_error(void) { return g_err.c_str(); }
+const char* hnswb200_version(void) { return "hnsw_b200 0.1 (sm_100a)"; }
+
+int hnswb200_create(hnswb200_index** out, int dim, int metric, int M, int ef_construction, uint64_t seed, int device) {
+  return guard([&] {
+    if (!out) fail(HNSWB200_EINVAL, "create: out is NULL");
+    *out = nullptr;
+    if (dim <= 0 || dim > 65536) fail(HNSWB200_EINVAL, "create: dim must be in 1..65536");
+    if (metric < 0 || metric > 2) fail(HNSWB200_EINVAL, "create: unknown metric");
+    if (M < 2 || M > 512) fail(HNSWB200_EINVAL, "create: num_connections must be in 2..512 (level_mult = 1/ln M)");
+    if (ef_construction < 1 || ef_construction > 4096) fail(HNSWB200_EINVAL, "create: num_nodes_search_construction must be in 1..4096");
+    hnswb200_index* x = new hnswb200_index();
+    x->dim = dim; x->metric = metric; x->M = M; x->efC = ef_construction; x->seed = seed; x->rng_state = seed;
+    x->device = device;
+    x->ld = round_up(dim, 4);
+    x->slots0 = 2 * M; x->slotsU = M;
+    try { init_device(x); } catch (...) { delete x; throw; }
+    *out = x;
+  });
+}
+
+int hnswb200_set_flavour(hnswb200_index* x, int flavour) {
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    if (flavour != HNSWB200_FLAVOUR_OHNSW && flavour != HNSWB200_FLAVOUR_HNSW_BA) fail(HNSWB200_EINVAL, "unknown flavour");
+    x->flavour = flavour;
+  });
+}
+
+int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
+  return guard([&] {
+    if (!x || !name) fail(HNSWB200_EINVAL, "index or name is NULL");
+    std::string s(name);
+    if (s == "hash_slots") x->param_hash_slots = value;
+    else if (s == "build_batch") x->param_build_batch = value;
+    else if (s == "warps_per_cta") x->param_warps_per_cta = value;
+    else fail(HNSWB200_EINVAL, "unknown parameter: " + s);
+  });
+}
+
+int hnswb200_destroy(hnswb200_index* x) {
+  return guard([&] {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    if (x->stream) cudaStreamSynchronize(x->stream);
+    if (x->ev0) cudaEventDestroy(x->ev0);
+    if (x->ev1) cudaEventDestroy(x->ev1);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+  });
+}
+
+int hnswb200_search(hnswb200_index* x, const float* queries, int64_t nq, int k, int ef, int mode, int32_t* ids, float* dists) {
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    if (nq > 0 && (!queries || !dists)) fail(HNSWB200_EINVAL, "search: queries/dists is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    if (x->n == 0 || x->entry < 0) fail(HNSWB200_EINVAL, "knn: empty hgraph");
+    if (nq <= 0) { if (nq < 0) fail(HNSWB200_EINVAL, "search: nq < 0"); return; }
+    if (k <= 0) fail(HNSWB200_EINVAL, "search: k must be > 0");
+    x->d_q.reserve((size_t)nq * x->ld);
+    x->d_ids.reserve((size_t)nq * k);
+    x->d_dists.reserve((size_t)nq * k);
+    upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, x->stream);
+    search_device(x, x->d_q.p, nq, k, ef, mode, x->d_ids.p, x->d_dists.p, x->stream, false);
+    if (ids) CUDA_CHECK(cudaMemcpyAsync(ids, x->d_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, x->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dists, x->d_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, x->stream));
+    unsigned long long evs[2];
+    CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost, x->stream));
+    CUDA_CHECK(cudaStreamSynchronize(x->stream));
+    x->st.search_visited_overflows = evs[0];
+    if (evs[1] && mode == HNSWB200_MODE_PARITY)
+      fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
+                               std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
+  });
+}
+
+int hnswb200_search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
+                           int32_t* d_ids, float* d_dists, void* stream) {
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    if (nq > 0 && (!d_queries || !d_dists)) fail(HNSWB200_EINVAL, "search_device: queries/dists is NULL");
+    if (x->ld != x->dim) fail(HNSWB200_EINVAL, "search_device: dim must be a multiple of 4 (rows are read with 128-bit loads)");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
+    search_device(x, d_queries, nq, k, ef, mode, d_ids, d_dists, s, stream == nullptr);
+  });
+}
+
+int hnswb200_last_search_counters(hnswb200_index* x, uint32_t* out, int64_t nq) {
+  return guard([&] {
+    if (!x || !out) fail(HNSWB200_EINVAL, "index or out is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    if (nq != x->last_nq) fail(HNSWB200_EINVAL, "last_search_counters: nq does not match the last search");
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(out, x->d_counters.p, (size_t)nq * 3 * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+int hnswb200_import_graph(hnswb200_index* x, const float* data, int64_t n, int id_base, int max_layer, int64_t entry,
+                          const int64_t* const* layer_offsets, const int32_t* const* layer_nbrs) {
+  return guard([&] {
+    if (!x || !data || !layer_offsets || !layer_nbrs) fail(HNSWB200_EINVAL, "import_graph: NULL argument");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    import_graph(x, data, n, id_base, max_layer, entry, layer_offsets, layer_nbrs);
+  });
+}
+
+int hnswb200_export_layer(hnswb200_index* x, int layer, int id_base, int64_t* offsets, int32_t* nbrs, int64_t* nnz) {
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    if (layer < 0 || layer > x->max_layer) fail(HNSWB200_EINVAL, "export_layer: no such layer");
+    CUDA_CHECK(cudaStreamSynchronize(x->stream));
+    std::vector<int32_t> rows; int slots = 0;
+    download_layer(x, layer, rows, slots);
+    int64_t o = 0;
+    for (int64_t i = 0; i < x->n; i++) {
+      const int32_t* row = layer_row(x, layer, rows, slots, i);
+      int d = row_degree(row, slots);
+      if (offsets) offsets[i] = o;
+      if (nbrs) for (int j = 0; j < d; j++) nbrs[o + j] = row[j] + id_base;
+      o += d;
+    }
+    if (offsets) offsets[x->n] = o;
+    if (nnz) *nnz = o;
+  });
+}
+
+int hnswb200_export_levels(hnswb200_index* x, int32_t* levels) {
+  return guard([&] {
+    if (!x || !levels) fail(HNSWB200_EINVAL, "index or levels is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    for (int64_t i = 0; i < x->n; i++) levels[i] = x->h_level[(size_t)i];
+  });
+}
+
+int hnswb200_get_info(hnswb200_index* x, hnswb200_info* out) {
+  return guard([&] {
+    if (!x || !out) fail(HNSWB200_EINVAL, "index or out is NULL");
+    out->n = x->n; out->dim = x->dim; out->metric = x->metric; out->M = x->M; out->ef_construction = x->efC;
+    out->max_layer = x->max_layer; out->entry_point = x->n ? x->entry : -1; out->slots0 = x->slots0;
+    out->slots_upper = x->slotsU; out->flavour = x->flavour; out->device = x->device;
+  });
+}
+
+int hnswb200_get_stats(hnswb200_index* x, hnswb200_stats* out) {
+  return guard([&] {
+    if (!x || !out) fail(HNSWB200_EINVAL, "index or out is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    hnswb200_stats& st = x->st;
+    // search counters: reduce the per-query rows of the last call
+    st.search_n_dist = st.search_n_exp0 = st.search_n_expU = 0;
+    if (x->last_nq > 0) {
+      std::vector<uint32_t> c((size_t)x->last_nq * 3);
+      CUDA_CHECK(cudaMemcpy(c.data(), x->d_counters.p, c.size() * 4, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < x->last_nq; i++) { st.search_n_dist += c[3 * i]; st.search_n_exp0 += c[3 * i + 1]; st.search_n_expU += c[3 * i + 2]; }
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, x->ev0, x->ev1) == cudaSuccess) st.search_kernel_ms = ms;
+      else cudaGetLastError();
+    }
+    // lib/hnsw.ml:732-751 counts distance calls; bytes per SURVEY.md 8d
+    st.search_algorithmic_bytes = (double)st.search_n_dist * 4.0 * x->dim + (double)st.search_n_exp0 * 4.0 * x->slots0 +
+                                  (double)st.search_n_expU * 4.0 * x->slotsU;
+    // Hgraph.Stats (lib/hnsw.ml:353-375)
+    st.num_layers = x->n ? x->max_layer + 1 : 0;
+    for (int l = 0; l < st.num_layers && l < 16; l++) {
+      std::vector<int32_t> rows; int slots = 0;
+      download_layer(x, l, rows, slots);
+      int64_t nodes = 0, iso = 0, sum = 0; int mn = 1 << 30, mx = -1;
+      for (int64_t i = 0; i < x->n; i++) {
+        const int32_t* row = layer_row(x, l, rows, slots, i);
+        if (!row) continue;
+        int d = row_degree(row, slots);
+        nodes++; sum += d; mn = std::min(mn, d); mx = std::max(mx, d); if (!d) iso++;
+      }
+      st.layer_nodes[l] = nodes; st.layer_min_degree[l] = nodes ? mn : 0; st.layer_max_degree[l] = nodes ? mx : 0;
+      st.layer_mean_degree[l] = nodes ? (double)sum / (double)nodes : 0.0; st.layer_isolated[l] = iso;
+    }
+    *out = st;
+  });
+}
+
+int hnswb200_recall(const float* expected, const float* got, int64_t nq, int k, double epsilon, double* out) {
+  return guard([&] {
+    // Recall.compute (benchmark/dataset.ml:105-127): trivial host arithmetic on two k x nq mats
+    if (!expected || !got || !out) fail(HNSWB200_EINVAL, "recall: NULL argument");
+    if (nq <= 0 || k <= 0) fail(HNSWB200_EINVAL, "Recall.compute: arrrays have unequal shapes");
+    double ret = 0.;
+    for (int64_t q = 0; q < nq; q++) {
+      int ok = 0;
+      for (int i = 0; i < k; i++)
+        if ((double)got[q * k + i] <= (double)expected[q * k + (k - 1)] + epsilon) ok++;
+      ret += (double)ok / (double)k;
+    }
+    *out = ret / (double)nq;
+  });
+}
+
+int hnswb200_host_register(const void* ptr, int64_t bytes) {
+  return guard([&] {
+    if (!ptr || bytes <= 0) fail(HNSWB200_EINVAL, "host_register: bad argument");
+    CUDA_CHECK(cudaHostRegister(const_cast<void*>(ptr), (size_t)bytes, cudaHostRegisterDefault));
+  });
+}
+int hnswb200_host_unregister(const void* ptr) {
+  return guard([&] {
+    if (!ptr) fail(HNSWB200_EINVAL, "host_unregister: NULL");
+    CUDA_CHECK(cudaHostUnregister(const_cast<void*>(ptr)));
+  });
+}
+
+}  // extern "C"
+
+#include "api_build.inl"
+#include "api_eval.inl"

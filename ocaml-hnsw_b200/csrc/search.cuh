@@ -1,0 +1,317 @@
+// Batched k-NN search: one warp per query, persistent warps pulling queries from a counter.
+//
+// Restates, per query, Ohnsw.knn (lib/ohnsw.ml:859-875): greedy descent through layers
+// max_layer..1 with search_one_simple (:492-508), then search_k on layer 0 (:543-588).
+// The sequential best-first semantics are kept exactly (PARITY): one expansion per iteration,
+// neighbours taken in list order, exact visited set, heaps ordered by (distance, id).  What is
+// parallel is everything inside one expansion: the adjacency row is one coalesced load, the
+// visited test-and-set runs one neighbour per lane, and the distances of all unvisited
+// neighbours are evaluated eight at a time (a team of 8 lanes per vector, 128-bit loads).
+//
+// Per-warp shared memory: the beam (`near`, <= ef sorted keys), a tie list, the compacted
+// neighbour ids/distances of the current expansion, the query, the visited hash.
+#pragma once
+#include "common.cuh"
+
+namespace hb {
+
+struct SearchParams {
+  GraphView g;
+  const float* queries;      // [nq][ld4*4]
+  int64_t nq;
+  int ef, k, ef_cap;
+  int accept_ties;           // Hnsw.Ba flavour: accept d <= top (lib/hnsw.ml:494-506)
+  int pad_inf;               // Hnsw.Ba flavour: +inf padding (lib/hnsw.ml:771)
+  int hash_slots;            // power of two
+  int q_smem_chunks;         // float4 slots reserved for the query copy
+  int smem_per_warp;
+  int32_t* out_ids;          // [nq][k] or null
+  float* out_dists;          // [nq][k]
+  uint32_t* counters;        // [nq][3]
+  unsigned int* next_query;  // work counter
+  uint32_t* bitset_pool;     // [pool_size][words]
+  int* pool_busy;
+  int pool_size;
+  int words;
+  unsigned long long* events; // [0] visited spills, [1] tie-list overflows
+};
+
+__host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, int q_chunks) {
+  return ef_cap * 8 + TIES_CAP * 8 + 32 * 4 + 32 * 4 + q_chunks * 16 + hash_slots * 4;
+}
+
+template <int CPL>
+struct WarpCtx {
+  uint64_t* keys;
+  uint64_t* ties;
+  uint32_t* newid;
+  float* newd;
+  float4* qs;
+  float4 q[CPL > 0 ? CPL : 1];
+  VisitedSet vis;
+  int lane;
+};
+
+__device__ __forceinline__ void visited_spill(VisitedSet& v, const SearchParams& p, int lane) {
+  int s = -1;
+  if (lane == 0) {
+    unsigned start = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % (unsigned)p.pool_size;
+    for (unsigned i = start;; i = (i + 1 == (unsigned)p.pool_size ? 0 : i + 1))
+      if (atomicCAS(&p.pool_busy[i], 0, 1) == 0) { s = (int)i; break; }
+    __threadfence();
+    atomicAdd(p.events, 1ull);
+  }
+  s = __shfl_sync(FULL, s, 0);
+  v.pool_slot = s;
+  v.bits = p.bitset_pool + (size_t)s * p.words;
+  for (uint32_t i = lane; i <= v.mask; i += 32) {
+    uint32_t key = v.tab[i];
+    if (key) { uint32_t id = key - 1u; atomicOr(&v.bits[id >> 5], 1u << (id & 31)); }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void visited_release(VisitedSet& v, const SearchParams& p, int lane) {
+  if (v.bits) {
+    for (int i = lane; i < p.words; i += 32) v.bits[i] = 0u;
+    __syncwarp();
+    __threadfence();
+    if (lane == 0) atomicExch(&p.pool_busy[v.pool_slot], 0);
+    v.bits = nullptr;
+  }
+}
+// true if `id` was not yet visited (and marks it).  Called by a subset of lanes.
+__device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id) {
+  if (v.bits) {
+    uint32_t bit = 1u << (id & 31);
+    return !(atomicOr(&v.bits[id >> 5], bit) & bit);
+  }
+  return hash_test_and_set(v.tab, v.mask, v.shift, id);
+}
+
+// search_k (lib/ohnsw.ml:543-588) on layer `layer`, beam already seeded with `n` keys (all
+// unexpanded, all marked visited).  Leaves the nearest set in keys[0..n).
+template <int CPL>
+__device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>& w, int layer, int& n,
+                                             uint32_t& n_dist, uint32_t& n_exp, bool& tie_overflow) {
+  const GraphView& g = p.g;
+  const int lane = w.lane;
+  const int ef = p.ef;
+  int fu = 0, ties_n = 0;
+  float top_d = n == ef ? key_dist(w.keys[ef - 1]) : 0.f;
+  while (true) {
+    // ---- MinQueue.pop_min visit_me (:565): smallest unexpanded key of near + live tie list
+    int pos = -1;
+    while (fu < n) {
+      int idx = fu + lane;
+      bool un = idx < n && !(w.keys[idx] & 1ull);
+      unsigned b = __ballot_sync(FULL, un);
+      if (b) { pos = fu + __ffs(b) - 1; break; }
+      fu += 32;
+    }
+    if (fu > n) fu = n;
+    uint64_t ck = pos >= 0 ? w.keys[pos] : KEY_INF;
+    bool from_ties = false;
+    if (ties_n > 0) {
+      uint64_t tk = lane < ties_n ? w.ties[lane] : KEY_INF;
+      uint64_t mn = tk;
+      for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }
+      if (mn < ck) {
+        unsigned who = __ballot_sync(FULL, tk == mn);
+        int sel = __ffs(who) - 1;
+        uint64_t lastk = w.ties[ties_n - 1];
+        __syncwarp();
+        if (lane == 0) w.ties[sel] = lastk;
+        ties_n--;
+        ck = mn; from_ties = true;
+        __syncwarp();
+      }
+    }
+    if (ck == KEY_INF) break;                      // visit_me empty (:566) or only dead entries (:568)
+    if (!from_ties) {
+      if (lane == 0) w.keys[pos] = ck | 1ull;
+      fu = pos + 1;
+      __syncwarp();
+    }
+    const uint32_t c = key_id(ck);
+    n_exp++;
+
+    // ---- Neighbours.iter (Graph.adjacent graph c.node) (:570), 32 list slots per round
+    const int slots = layer == 0 ? g.slots0 : g.slotsU;
+    const int32_t* row;
+    if (layer == 0) row = g.adj0 + (size_t)c * g.slots0;
+    else { int off = g.upper_off[c]; row = off < 0 ? nullptr : g.adjU + ((size_t)off + layer - 1) * g.slotsU; }
+    for (int r0 = 0; r0 < slots && row; r0 += 32) {
+      int nb = (r0 + lane < slots) ? __ldg(row + r0 + lane) : -1;
+      unsigned valid = __ballot_sync(FULL, nb >= 0);
+      if (!valid) break;
+      if (!w.vis.bits && w.vis.count + 32u > w.vis.limit) visited_spill(w.vis, p, lane);
+      bool is_new = nb >= 0 && visited_test_and_set(w.vis, (uint32_t)nb);   // Visited.mem / add (:571-572)
+      unsigned m = __ballot_sync(FULL, is_new);
+      int cnt = __popc(m);
+      w.vis.count += cnt;
+      if (cnt) {
+        if (is_new) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
+        __syncwarp();
+        batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);          // MinQueue.element (:573)
+        n_dist += cnt;
+        // ---- accept in list order (:574-578)
+        float t = lane < cnt ? w.newd[lane] : 0.f;
+        uint32_t id = lane < cnt ? w.newid[lane] : 0u;
+        int done = -1;
+        while (true) {
+          bool want = lane < cnt && lane > done &&
+                      (n < ef || (p.accept_ties ? t <= top_d : t < top_d));
+          unsigned wm = __ballot_sync(FULL, want);
+          if (!wm) break;
+          int L = __ffs(wm) - 1;
+          done = L;
+          float tL = __shfl_sync(FULL, t, L);
+          uint32_t idL = __shfl_sync(FULL, id, L);
+          uint64_t ev = beam_insert(w.keys, n, ef, make_key(tL, idL), lane, fu);
+          __syncwarp();
+          if (n == ef) {
+            float new_top = key_dist(w.keys[ef - 1]);
+            if (ev) {                               // Heap.pop_exn nearest_maxq (:577)
+              // the evicted element stays in visit_me; it can still be popped and expanded iff
+              // its distance equals the (new) top (stop rule is a strict >, :568)
+              if (new_top < key_dist(ev)) ties_n = 0;
+              else if (!(ev & 1ull)) {
+                if (ties_n < TIES_CAP) { if (lane == 0) w.ties[ties_n] = ev; ties_n++; }
+                else tie_overflow = true;
+              }
+            }
+            top_d = new_top;
+          }
+          __syncwarp();
+        }
+      }
+      if (valid != FULL) break;                     // row ended inside this round
+    }
+  }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GraphView& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tl = lane & (TEAM - 1);
+  unsigned char* my = smem_raw + (size_t)warp * p.smem_per_warp;
+  WarpCtx<CPL> w;
+  w.lane = lane;
+  w.keys = reinterpret_cast<uint64_t*>(my);
+  w.ties = w.keys + p.ef_cap;
+  w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
+  w.newd = reinterpret_cast<float*>(w.newid + 32);
+  w.qs = reinterpret_cast<float4*>(w.newd + 32);
+  w.vis.tab = reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks);
+  w.vis.mask = (uint32_t)p.hash_slots - 1u;
+  w.vis.shift = 32u - (uint32_t)__ffs(p.hash_slots) + 1u;
+  w.vis.limit = (uint32_t)p.hash_slots / 2u + (uint32_t)p.hash_slots / 8u;   // load <= 0.625
+  w.vis.bits = nullptr;
+  w.vis.pool_slot = -1;
+
+  while (true) {
+    unsigned qi = 0;
+    if (lane == 0) qi = atomicAdd(p.next_query, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= (unsigned)p.nq) break;
+
+    // target -> registers (and shared for the generic path)
+    const float4* qrow = reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4;
+    if (CPL > 0) {
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        int ch = tl + TEAM * c;
+        w.q[c] = ch < g.chunks ? __ldg(qrow + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int ch = lane; ch < g.chunks; ch += 32) w.qs[ch] = __ldg(qrow + ch);
+    }
+    visited_clear(w.vis, lane);
+
+    uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
+    bool tie_overflow = false;
+
+    // ---- knn (:859-875): entry point, greedy descent (search_one_simple :492-508)
+    uint32_t cur = (uint32_t)g.entry;
+    if (lane == 0) w.newid[0] = cur;
+    __syncwarp();
+    batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, 1, lane);
+    float d_cur = w.newd[0];
+    __syncwarp();
+    for (int layer = g.max_layer; layer >= 1; layer--) {
+      n_dist++;                                     // best_distance = distance (value start) target (:496)
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        int off = g.upper_off[cur];
+        const int32_t* row = off < 0 ? nullptr : g.adjU + ((size_t)off + layer - 1) * g.slotsU;
+        n_expU++;
+        uint64_t best = KEY_INF;                    // (distance, list position) of the running minimum
+        uint32_t best_id = 0;
+        for (int r0 = 0; r0 < g.slotsU && row; r0 += 32) {
+          int nb = (r0 + lane < g.slotsU) ? __ldg(row + r0 + lane) : -1;
+          unsigned m = __ballot_sync(FULL, nb >= 0);
+          int cnt = __popc(m);
+          if (!cnt) break;
+          if (nb >= 0) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
+          __syncwarp();
+          batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);
+          n_dist += cnt;
+          uint64_t mine = lane < cnt ? (((uint64_t)f2ord(w.newd[lane]) << 32) | (uint32_t)(r0 + lane)) : KEY_INF;
+          uint64_t mn = mine;
+          for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }
+          if (mn < best) {
+            best = mn;
+            int src = __ffs(__ballot_sync(FULL, mine == mn)) - 1;
+            best_id = w.newid[src];
+          }
+          __syncwarp();
+          if (m != FULL) break;
+        }
+        // the scan moves `best` on every strictly closer neighbour (:502): it ends on the first
+        // occurrence of the row minimum, if that is strictly closer than the current node
+        if (best != KEY_INF) {
+          float bd = ord2f((uint32_t)(best >> 32));
+          if (bd < d_cur) { d_cur = bd; cur = best_id; changed = true; }
+        }
+      }
+    }
+
+    // ---- search_k on layer 0 seeded with {node} (:870-873)
+    n_dist++;                                       // MinQueue.add_node w_queue !node
+    if (lane == 0) w.keys[0] = make_key(d_cur, cur);
+    int n = 1;
+    visited_test_and_set(w.vis, lane == 0 ? cur : cur);   // all lanes race on the same slot: one wins
+    w.vis.count = 1;
+    __syncwarp();
+    layer_search<CPL>(p, w, 0, n, n_dist, n_exp0, tie_overflow);
+
+    // ---- pop ascending into the result rows (:886-893)
+    for (int i = lane; i < p.k; i += 32) {
+      int32_t oid = -1;
+      float od = p.pad_inf ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000);
+      if (i < n) {
+        uint64_t key = w.keys[i];
+        oid = (int32_t)key_id(key);
+        float d = key_dist(key);
+        od = g.metric == 0 ? (float)sqrt((double)d) : d;   // Float.sqrt in double, fp32 store (:889,:899)
+      }
+      if (p.out_ids) p.out_ids[(size_t)qi * p.k + i] = oid;
+      p.out_dists[(size_t)qi * p.k + i] = od;
+    }
+    if (lane == 0) {
+      if (p.counters) {
+        p.counters[(size_t)qi * 3 + 0] = n_dist;
+        p.counters[(size_t)qi * 3 + 1] = n_exp0;
+        p.counters[(size_t)qi * 3 + 2] = n_expU;
+      }
+      if (tie_overflow) atomicAdd(p.events + 1, 1ull);
+    }
+    visited_release(w.vis, p, lane);
+    __syncwarp();
+  }
+}
+
+}  // namespace hb

@@ -1,0 +1,171 @@
+"""GPU search vs the oracle on oracle-built graphs (the 'graph built by the reference, exported
+to the GPU layout' check): ids, distances and work counters must be identical, bit for bit.
+
+All calls go through the C ABI (ctypes) via the Ohnsw mirror."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ocaml_hnsw_b200 as H
+from ocaml_hnsw_b200 import Ohnsw, capi
+from oracle import oracle as O
+from tests.util import assert_same_results, draw_levels, grid36, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_index(X, M, efC, metric=O.METRIC_L2, seed=7):
+    o = O.VecOracle(X.shape[1], metric)
+    o.build(X, M, efC, draw_levels(len(X), M, seed))
+    return o
+
+
+def _gpu_from(o, X, M, efC, metric=capi.L2):
+    h = Ohnsw.Hgraph(X.shape[1], metric, M, efC)
+    h.import_graph(X, o.export())
+    return h
+
+
+def _check(o, h, Q, k, ef):
+    ids_o, d_o, cnt_o = o.search(Q, k, ef, counters=True)
+    ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=k, ef=ef)
+    assert_same_results(ids_g, d_g, ids_o, d_o)
+    cnt_g = h.last_search_counters(len(Q))
+    assert np.array_equal(cnt_g.astype(np.uint64), cnt_o), "work counters (n_dist, n_exp0, n_expU) differ"
+    return ids_g, d_g
+
+
+@pytest.fixture(scope="module")
+def uni2k():
+    X = uniform(2000, 128, 1234)
+    Q = uniform(300, 128, 4321)
+    o = _oracle_index(X, 16, 100)
+    return X, Q, o, _gpu_from(o, X, 16, 100)
+
+
+@pytest.mark.parametrize("k,ef", [(10, 10), (10, 50), (10, 200), (1, 1), (50, 50), (3, 33), (100, 512)])
+def test_uniform_128(uni2k, k, ef):
+    X, Q, o, h = uni2k
+    _check(o, h, Q, k, ef)
+
+
+def test_graph_roundtrip_through_gpu_layout(uni2k):
+    X, Q, o, h = uni2k
+    g0, g1 = o.export(), h.export_graph()
+    assert (g1.n, g1.max_layer, g1.entry) == (g0.n, g0.max_layer, g0.entry)
+    for l in range(g0.max_layer + 1):
+        assert np.array_equal(g0.offsets[l], g1.offsets[l]) and np.array_equal(g0.nbrs[l], g1.nbrs[l])
+    st = h.stats()
+    assert st.num_layers == g0.max_layer + 1 and st.layer_nodes[0] == 2000
+    assert st.layer_max_degree[0] <= 32 and st.layer_isolated[0] == 0
+
+
+def test_visited_spill_is_exact(uni2k):
+    """Tiny visited hash: every query outgrows shared memory and continues on the global bitset."""
+    X, Q, o, _ = uni2k
+    h = _gpu_from(o, X, 16, 100)
+    h.set_param("hash_slots", 1024)
+    _check(o, h, Q, 10, 200)
+    assert h.stats().search_visited_overflows > 0
+
+
+def test_grid36_fixture():
+    """test/test.ml: 36-point 2-D grid, M=3, efC=20, k=3 (dim 2 -> padded rows)."""
+    X = grid36()
+    Q = uniform(10, 2, 5) * 3 + 2.5
+    o = _oracle_index(X, 3, 20)
+    h = _gpu_from(o, X, 3, 20)
+    _check(o, h, Q, 3, 3)
+    _check(o, h, Q, 3, 20)
+
+
+def test_integer_data_with_exact_ties():
+    """SIFT-like integer coordinates: squared distances are exact integers, ties are common;
+    exercises the (distance, id) order and the evicted-tie list."""
+    rng = np.random.default_rng(11)
+    X = rng.integers(0, 4, (3000, 16)).astype(np.float32)      # many equal distances, many duplicates
+    Q = rng.integers(0, 4, (200, 16)).astype(np.float32)
+    o = _oracle_index(X, 8, 40)
+    h = _gpu_from(o, X, 8, 40)
+    for k, ef in [(10, 10), (10, 40), (5, 100)]:
+        _check(o, h, Q, k, ef)
+
+
+def test_sift_like_128():
+    X = H.sift_like(4000, 128, seed=1234)
+    Q = H.sift_like(200, 128, seed=4321)
+    o = _oracle_index(X, 16, 100)
+    h = _gpu_from(o, X, 16, 100)
+    ids, _ = _check(o, h, Q, 10, 64)
+    gt, _ = O.bruteforce(X, Q, 10)
+    assert H.Recall.ids(gt, ids) > 0.9
+
+
+@pytest.mark.parametrize("dim,M,metric", [(1, 4, capi.L2), (3, 4, capi.L2), (96, 16, capi.L2), (100, 24, capi.ANGULAR),
+                                          (100, 24, capi.IP), (200, 8, capi.L2), (960, 16, capi.L2)])
+def test_other_shapes(dim, M, metric):
+    n = 1200 if dim < 900 else 600
+    X = uniform(n, dim, 21)
+    Q = uniform(64, dim, 22)
+    if metric != capi.L2:
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    o = _oracle_index(X, M, 60, metric)
+    h = _gpu_from(o, X, M, 60, metric)
+    _check(o, h, Q, 10, 10)
+    _check(o, h, Q, 10, 80)
+
+
+def test_fewer_than_k_results_are_padded():
+    X = uniform(7, 8, 1)
+    o = _oracle_index(X, 4, 10)
+    h = _gpu_from(o, X, 4, 10)
+    ids, d = _check(o, h, uniform(5, 8, 2), 12, 12)
+    assert (ids[:, 7:] == -1).all() and np.isnan(d[:, 7:]).all()        # lib/ohnsw.ml:879-881
+
+
+def test_empty_hgraph_raises():
+    h = Ohnsw.Hgraph(8)
+    with pytest.raises(ValueError, match="knn: empty hgraph"):          # lib/ohnsw.ml:862
+        Ohnsw.knn_batch_bigarray(h, np.zeros((1, 8), np.float32), k=1)
+    with pytest.raises(ValueError, match="knn: empty hgraph"):
+        Ohnsw.knn(h, Ohnsw.Visited.create(0), k=1, target=np.zeros(8, np.float32))
+
+
+def test_reference_inline_goldens_on_gpu(golden_dir):
+    """TestSearchK (lib/ohnsw.ml:593-644) run through the GPU: 1-D values as dim-1 vectors, the
+    start node as entry point of a single-layer imported graph."""
+    cases = json.load(open(os.path.join(golden_dir, "ohnsw_inline_tests.json")))["search_k"]
+    for case in cases:
+        vals = np.array(case["values"], np.float32)[:, None]
+        n = len(vals)
+        if case["graph"] == "ring":
+            a = O.AbsOracle(case["values"]); a.layer_create_loop(0)
+            rows = [a.adjacent(0, i) for i in range(n)]
+        else:
+            rows = [[] for _ in range(n)]
+        offs = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+        nbrs = np.array([x for r in rows for x in r], np.int32)
+        g = H.FlatGraph(n, 0, case["start"], [offs], [nbrs])
+        h = Ohnsw.Hgraph(1, capi.L2, 2, 10).import_graph(vals, g)
+        k = case["k"]
+        ids, d = Ohnsw.knn_batch_bigarray(h, np.array([[case["target"]]], np.float32), k=k)
+        got = [(int(i), float(x)) for i, x in zip(ids[0], d[0]) if i >= 0]
+        assert [i for i, _ in got] == [i for i, _ in case["expect"]], case
+        assert np.allclose([x for _, x in got], [x for _, x in case["expect"]], rtol=1e-6, atol=1e-6)
+
+
+def test_import_validation():
+    h = Ohnsw.Hgraph(4, capi.L2, 4, 10)
+    X = uniform(3, 4, 1)
+    bad = H.FlatGraph(3, 0, 0, [np.array([0, 2, 2, 2])], [np.array([1, 1], np.int32)])
+    with pytest.raises(ValueError, match="duplicate"):
+        h.import_graph(X, bad)
+    bad = H.FlatGraph(3, 0, 5, [np.array([0, 0, 0, 0])], [np.zeros(0, np.int32)])
+    with pytest.raises(ValueError, match="invalid node"):                # lib/ohnsw.ml:343
+        h.import_graph(X, bad)
+    bad = H.FlatGraph(3, 0, 0, [np.array([0, 1, 1, 1])], [np.array([9], np.int32)])
+    with pytest.raises(ValueError, match="out of range"):
+        h.import_graph(X, bad)
