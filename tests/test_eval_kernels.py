@@ -20,13 +20,21 @@ def _same_up_to_ties(ids_a, d_a, ids_b, d_b):
             assert abs(d_a[i, j] - d_b[i, j]) <= REL * max(d_a[i, j], 1e-6)
 
 
-@pytest.mark.parametrize("n,nq,dim,k", [(5000, 100, 128, 10), (777, 13, 7, 5), (3000, 70, 100, 100), (50, 4, 960, 64)])
+@pytest.mark.parametrize("n,nq,dim,k", [(5000, 100, 128, 10), (777, 13, 7, 5), (3000, 70, 100, 100), (90, 4, 960, 64)])
 def test_bruteforce_matches_oracle(n, nq, dim, k):
     X, Q = uniform(n, dim, 3), uniform(nq, dim, 4)
     ids_o, d_o = O.bruteforce(X, Q, k)
     ids_g, d_g = H.brute_force_knn_l2(X, Q, k, return_ids=True)
     _same_up_to_ties(ids_g, d_g, ids_o, d_o)
-    assert H.Recall.compute(d_o, d_g, epsilon=1e-5) > 0.999
+    assert H.Recall.compute(d_o, d_g, epsilon=1e-4) > 0.999
+
+
+def test_bruteforce_pads_when_k_exceeds_n():
+    X, Q = uniform(20, 16, 3), uniform(3, 16, 4)
+    ids_g, d_g = H.brute_force_knn_l2(X, Q, 32, return_ids=True)
+    ids_o, d_o = O.bruteforce(X, Q, 32)
+    assert (ids_g[:, 20:] == -1).all() and np.isnan(d_g[:, 20:]).all()
+    _same_up_to_ties(ids_g, d_g, ids_o, d_o)
 
 
 def test_bruteforce_integer_data_is_exact():
