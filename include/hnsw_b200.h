@@ -178,10 +178,12 @@ int hnswb200_recall(const float* expected, const float* got, int64_t nq, int k, 
 /* ---- multi-GPU: per-shard top-k merge ------------------------------------------ */
 
 /* After an all-gather of per-shard results: d_ids/d_dists are `[n_shards][nq][k]` in device
- * memory (ids already global), merged into the k best per query `[nq][k]`, ascending by
- * (distance, id), -1/NaN padded. */
+ * memory, ids local to each shard; `shard_offsets` (host, int64[n_shards], NULL = all zero) is
+ * the first global row of each shard.  Merged into the k best per query `[nq][k]` with global
+ * ids, ascending by (distance, id), -1/NaN padded.  `stream` NULL = default stream, synchronous. */
 int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n_shards, int64_t nq,
-                               int k, int32_t* d_out_ids, float* d_out_dists, void* stream);
+                               int k, const int64_t* shard_offsets, int32_t* d_out_ids,
+                               float* d_out_dists, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 

@@ -58,7 +58,7 @@ SIGNATURES = {
     "hnswb200_export_levels": (_i32, [_vp, _vp]),
     "hnswb200_bruteforce_knn": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hnswb200_recall": (_i32, [_vp, _vp, _i64, _i32, _f64, C.POINTER(_f64)]),
-    "hnswb200_merge_topk_device": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "hnswb200_merge_topk_device": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "hnswb200_get_info": (_i32, [_vp, C.POINTER(Info)]),
     "hnswb200_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "hnswb200_host_register": (_i32, [_vp, _i64]),
@@ -106,3 +106,12 @@ def as_mat(a, dim=None):
     if dim is not None and a.shape[1] != dim:
         raise ValueError(f"vector dimension {a.shape[1]} does not match the index dimension {dim}")
     return a
+
+
+def host_register(a):
+    """Pin a caller buffer (the payload of a Bigarray) so H2D / D2H copies are asynchronous DMA."""
+    check(lib().hnswb200_host_register(ptr(a), a.nbytes))
+
+
+def host_unregister(a):
+    check(lib().hnswb200_host_unregister(ptr(a)))

@@ -1,11 +1,317 @@
-// C ABI: index construction (included by hnsw_b200.cu).
+// C ABI: index construction (included by hnsw_b200.cu).  Host orchestration of build.cuh:
+// level draw, storage growth, the batch schedule and the three phases per batch.
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+// lib/ohnsw.ml:781 — level = round_nearest(-ln U * mL), U uniform; the reference draws U from
+// OCaml's global Random state, which cannot be reproduced: callers that compare against a
+// reference/oracle build pass the levels in.  Same splitmix64 stream as the oracle's draw_level.
+int draw_level(hnswb200_index* x) {
+  x->rng_state += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x->rng_state;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  double u = ((double)(z >> 11) + 1.0) * (1.0 / 9007199254740992.0);   // (0, 1]
+  double mL = 1.0 / std::log((double)x->M);                             // :844
+  return (int)std::floor(-std::log(u) * mL + 0.5);
+}
+
+struct BuildPlan {
+  SearchPlan sp;
+  int sel_cap, ucap, link_warps, link_smem_per_warp, link_grid_per_sm;
+  int sel0, selU, cap0, capU, keep_all;
+};
+
+BuildPlan plan_build(hnswb200_index* x) {
+  BuildPlan bp;
+  const bool ba = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
+  bp.sel0 = ba ? x->M : 2 * x->M;              // lib/ohnsw.ml:818 vs lib/hnsw.ml:753-758 (Q3)
+  bp.selU = x->M;
+  bp.cap0 = 2 * x->M; bp.capU = x->M;
+  bp.keep_all = ba ? 1 : 0;
+  int max_slots = std::max(x->slots0, x->slotsU);
+  bp.sel_cap = round_up(std::max(max_slots, 4), 4);
+  bp.ucap = round_up(max_slots + hb::LINK_MCAP, 4);
+  // phase 1: the search plan for ef = efC plus the second target copy and the selected list
+  SearchPlan& pl = bp.sp;
+  int ef = x->efC;
+  int chunks = x->ld / 4;
+  int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
+  pl.cpl = cpl <= 4 ? cpl : 0;
+  pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
+  pl.ef_cap = round_up(ef, 32);
+  int extra = pl.q_chunks * 16 + bp.sel_cap * 4;
+  int hs = x->param_hash_slots > 0 ? next_pow2((int)x->param_hash_slots) : next_pow2(std::max(1024, 32 * ef));
+  hs = std::min(hs, 32768);
+  while (hs > 1024 && hb::search_smem_per_warp(pl.ef_cap, hs, pl.q_chunks) + extra > x->max_smem_optin) hs >>= 1;
+  pl.hash_slots = hs;
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, hs, pl.q_chunks) + extra;
+  if (pl.smem_per_warp > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
+  // pack the SM: as many warps as shared memory allows (<= 32), split into CTAs of <= 8 warps
+  int per_sm_warps = std::max(1, std::min(32, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 128))));
+  int ctas = (per_sm_warps + 7) / 8;
+  pl.warps = std::max(1, per_sm_warps / ctas);
+  while (pl.warps > 1 && (size_t)pl.warps * pl.smem_per_warp > (size_t)x->max_smem_optin) pl.warps--;
+  pl.smem = (size_t)pl.warps * pl.smem_per_warp;
+  pl.grid = x->num_sms * std::max(1, (int)((size_t)(227 * 1024) / (pl.smem + 1024)));
+  // phase 2
+  bp.link_smem_per_warp = hb::link_smem_per_warp(bp.ucap, bp.sel_cap, pl.q_chunks);
+  bp.link_warps = 8;
+  while (bp.link_warps > 1 && (size_t)bp.link_warps * bp.link_smem_per_warp > (size_t)x->max_smem_optin) bp.link_warps--;
+  if ((size_t)bp.link_smem_per_warp > (size_t)x->max_smem_optin) fail(HNSWB200_EINVAL, "build: dimension / num_connections too large for shared memory");
+  bp.link_grid_per_sm = std::max(1, std::min(4, (int)((size_t)(227 * 1024) / ((size_t)bp.link_warps * bp.link_smem_per_warp + 1024))));
+  return bp;
+}
+
+template <int CPL>
+void launch_build_search(const hb::BuildParams& p, const SearchPlan& pl, int grid, cudaStream_t s) {
+  CUDA_CHECK(cudaFuncSetAttribute(hb::build_search_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  hb::build_search_kernel<CPL><<<grid, pl.warps * 32, pl.smem, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+template <int CPL>
+void launch_build_link(const hb::BuildParams& p, int warps, size_t smem, int grid, cudaStream_t s) {
+  CUDA_CHECK(cudaFuncSetAttribute(hb::build_link_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hb::build_link_kernel<CPL><<<grid, warps * 32, smem, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void sort_keys(hnswb200_index* x, const uint64_t* in, uint64_t* out, unsigned n, int end_bit) {
+  size_t bytes = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int)n, 0, end_bit, x->stream));
+  x->b_cub.reserve_geo(bytes + 16);
+  CUDA_CHECK(cub::DeviceRadixSort::SortKeys(x->b_cub.p, bytes, in, out, (int)n, 0, end_bit, x->stream));
+  x->st.gpu_launches += 3;
+}
+
+enum { CTR_REQ = 0, CTR_REM = 1, CTR_HEADS = 2, CTR_NEXT = 3, CTR_N = 4 };
+
+// One batch: nodes [n0, n0 + B) against the graph of nodes [0, n0).
+void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, int64_t n_total) {
+  cudaStream_t s = x->stream;
+  const SearchPlan& pl = bpl.sp;
+  // request capacity: one per selected neighbour per layer
+  size_t req_cap = 0;
+  for (int64_t j = 0; j < B; j++)
+    req_cap += (size_t)bpl.sel0 + (size_t)std::min<int>(x->h_level[(size_t)(n0 + j)], x->max_layer) * bpl.selU;
+  x->b_req.reserve_geo(req_cap); x->b_req_sorted.reserve_geo(req_cap); x->b_heads.reserve_geo(req_cap);
+  CUDA_CHECK(cudaMemsetAsync(x->b_ctr.p, 0, CTR_N * sizeof(unsigned int), s));
+
+  hb::BuildParams p{};
+  hb::SearchParams& sp = p.sp;
+  sp.g = x->view();
+  sp.queries = nullptr; sp.nq = B; sp.ef = x->efC; sp.k = x->efC; sp.ef_cap = pl.ef_cap;
+  sp.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA; sp.pad_inf = 0;
+  sp.hash_slots = pl.hash_slots; sp.q_smem_chunks = pl.q_chunks; sp.smem_per_warp = pl.smem_per_warp;
+  sp.out_ids = nullptr; sp.out_dists = nullptr; sp.counters = nullptr; sp.next_query = nullptr;
+  sp.bitset_pool = x->d_bitpool.p; sp.pool_busy = x->d_pool_busy.p; sp.pool_size = x->pool_size; sp.words = x->pool_words;
+  sp.events = x->d_events.p;
+  p.adj0 = x->adj0.p; p.adjU = x->adjU.p; p.level = x->level.p; p.row_owner = x->row_owner.p;
+  p.n0 = (int)n0; p.B = (int)B;
+  p.sel0 = bpl.sel0; p.selU = bpl.selU; p.cap0 = bpl.cap0; p.capU = bpl.capU; p.keep_all = bpl.keep_all;
+  p.sel_cap = bpl.sel_cap; p.ucap = bpl.ucap; p.smem_per_warp = pl.smem_per_warp;
+  p.req = x->b_req.p; p.req_count = x->b_ctr.p + CTR_REQ;
+  p.rem_count = x->b_ctr.p + CTR_REM; p.head_count = x->b_ctr.p + CTR_HEADS; p.next = x->b_ctr.p + CTR_NEXT;
+  p.heads = x->b_heads.p; p.counters = x->b_counters.p;
+
+  // ---- phase 1
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (B + pl.warps - 1) / pl.warps));
+  switch (pl.cpl) {
+    case 1: launch_build_search<1>(p, pl, grid, s); break;
+    case 2: launch_build_search<2>(p, pl, grid, s); break;
+    case 3: launch_build_search<3>(p, pl, grid, s); break;
+    case 4: launch_build_search<4>(p, pl, grid, s); break;
+    default: launch_build_search<0>(p, pl, grid, s); break;
+  }
+  x->st.gpu_launches += 1;
+  unsigned ctr[CTR_N];
+  CUDA_CHECK(cudaMemcpyAsync(ctr, x->b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  unsigned n_req = ctr[CTR_REQ];
+  if (n_req > req_cap) fail(HNSWB200_ECUDA, "build: request buffer overrun");
+  if (n_req == 0) return;
+
+  // ---- phase 2: sort by row, one warp per row
+  sort_keys(x, x->b_req.p, x->b_req_sorted.p, n_req, 32 + hb::REQ_VBITS);
+  CUDA_CHECK(cudaMemsetAsync(x->b_ctr.p + CTR_HEADS, 0, 2 * sizeof(unsigned int), s));   // heads, next
+  hb::segment_heads_kernel<<<(n_req + 255) / 256, 256, 0, s>>>(x->b_req_sorted.p, n_req, hb::REQ_VBITS, x->b_heads.p,
+                                                               x->b_ctr.p + CTR_HEADS);
+  CUDA_CHECK(cudaGetLastError());
+  size_t rem_cap = (size_t)n_req * (size_t)(std::max(x->slots0, x->slotsU) + 1);
+  rem_cap = std::min<size_t>(rem_cap, (size_t)0xfffffff0u);
+  x->b_rem.reserve_geo(rem_cap); x->b_rem_sorted.reserve_geo(rem_cap);
+  p.req = x->b_req_sorted.p; p.n_req = n_req;
+  p.rem = x->b_rem.p; p.rem_cap = (unsigned)rem_cap;
+  p.smem_per_warp = bpl.link_smem_per_warp;
+  size_t link_smem = (size_t)bpl.link_warps * bpl.link_smem_per_warp;
+  int lgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * bpl.link_grid_per_sm, (n_req + bpl.link_warps - 1) / bpl.link_warps));
+  switch (pl.cpl) {
+    case 1: launch_build_link<1>(p, bpl.link_warps, link_smem, lgrid, s); break;
+    case 2: launch_build_link<2>(p, bpl.link_warps, link_smem, lgrid, s); break;
+    case 3: launch_build_link<3>(p, bpl.link_warps, link_smem, lgrid, s); break;
+    case 4: launch_build_link<4>(p, bpl.link_warps, link_smem, lgrid, s); break;
+    default: launch_build_link<0>(p, bpl.link_warps, link_smem, lgrid, s); break;
+  }
+  x->st.gpu_launches += 2;
+  CUDA_CHECK(cudaMemcpyAsync(ctr, x->b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  unsigned n_rem = ctr[CTR_REM];
+  if (n_rem > rem_cap) fail(HNSWB200_ECUDA, "build: removal buffer overrun");
+  if (n_rem == 0) return;
+
+  // ---- phase 3: sort removals by row, one warp per row
+  sort_keys(x, x->b_rem.p, x->b_rem_sorted.p, n_rem, 32 + hb::REM_ABITS);
+  CUDA_CHECK(cudaMemsetAsync(x->b_ctr.p + CTR_HEADS, 0, 2 * sizeof(unsigned int), s));
+  x->b_heads.reserve_geo(n_rem);
+  p.heads = x->b_heads.p;
+  hb::segment_heads_kernel<<<(n_rem + 255) / 256, 256, 0, s>>>(x->b_rem_sorted.p, n_rem, hb::REM_ABITS, x->b_heads.p,
+                                                               x->b_ctr.p + CTR_HEADS);
+  CUDA_CHECK(cudaGetLastError());
+  p.rem = x->b_rem_sorted.p; p.n_req = n_rem;
+  int ugrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * 8, (n_rem + 7) / 8));
+  hb::build_unlink_kernel<<<ugrid, 256, 0, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+  x->st.gpu_launches += 2;
+  (void)n_total;
+}
+
+// Append n_new vectors: Ohnsw.build_batch_bigarray on an empty index (lib/ohnsw.ml:840-857), a run
+// of Ohnsw.insert calls otherwise (:766-837).
+void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int32_t* levels) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (n_new < 0) fail(HNSWB200_EINVAL, "build: n < 0");
+  if (n_new == 0) return;
+  if (!data) fail(HNSWB200_EINVAL, "build: data is NULL");
+  const int64_t n_old = x->n, n_tot = n_old + n_new;
+  if (n_tot >= (int64_t(1) << 31) - 1) fail(HNSWB200_EINVAL, "build: too many nodes");
+  cudaStream_t s = x->stream;
+
+  // levels, upper-row bookkeeping (host mirrors are authoritative)
+  std::vector<int8_t> lvl_new((size_t)n_new);
+  for (int64_t i = 0; i < n_new; i++) {
+    int l = levels ? levels[i] : draw_level(x);
+    if (n_old + i == 0) l = 0;                       // the first node is the entry of layer 0 (:774-778)
+    if (l < 0 || l > 15) fail(HNSWB200_EINVAL, "build: level must be in 0..15");
+    lvl_new[(size_t)i] = (int8_t)l;
+  }
+  const int64_t rows_old = x->rowsU;
+  int64_t rows = rows_old;
+  std::vector<int32_t> uoff_new((size_t)n_new, -1), owner_new;
+  for (int64_t i = 0; i < n_new; i++)
+    if (lvl_new[(size_t)i] > 0) {
+      uoff_new[(size_t)i] = (int32_t)rows;
+      rows += lvl_new[(size_t)i];
+      owner_new.insert(owner_new.end(), (size_t)lvl_new[(size_t)i], (int32_t)(n_old + i));
+    }
+  if (rows >= (int64_t(1) << 31)) fail(HNSWB200_EINVAL, "build: too many upper-layer rows");
+  if (x->h_row_owner.size() != (size_t)rows_old) {   // graph came from import_graph: rebuild the owner map
+    x->h_row_owner.assign((size_t)rows_old, 0);
+    for (int64_t i = 0; i < n_old; i++)
+      for (int l = 0; l < x->h_level[(size_t)i]; l++) x->h_row_owner[(size_t)x->h_upper_off[(size_t)i] + l] = (int32_t)i;
+    x->row_owner.release();
+  }
+
+  // storage: grow geometrically so a run of single inserts stays linear
+  int64_t cap = x->cap, capU = x->capU;
+  if (n_tot > cap) cap = std::max<int64_t>(n_tot, cap + cap / 2);
+  if (rows > capU) capU = std::max<int64_t>(rows, capU + capU / 2);
+  const bool fresh = n_old == 0;
+  {
+    const int64_t old_cap = x->vec.n / std::max(1, x->ld), old_capU = x->adjU.n / std::max(1, x->slotsU);
+    x->vec.reserve((size_t)cap * x->ld, !fresh, s);
+    x->adj0.reserve((size_t)cap * x->slots0, !fresh, s);
+    x->upper_off.reserve((size_t)cap, !fresh, s);
+    x->level.reserve((size_t)cap, !fresh, s);
+    x->adjU.reserve((size_t)std::max<int64_t>(capU, 1) * x->slotsU, !fresh, s);
+    bool owner_realloc = (size_t)std::max<int64_t>(capU, 1) > x->row_owner.n;
+    x->row_owner.reserve((size_t)std::max<int64_t>(capU, 1), false, s);
+    if (owner_realloc && rows_old > 0)
+      CUDA_CHECK(cudaMemcpyAsync(x->row_owner.p, x->h_row_owner.data(), (size_t)rows_old * 4, cudaMemcpyHostToDevice, s));
+    x->cap = cap; x->capU = std::max<int64_t>(capU, 1);
+    (void)old_cap; (void)old_capU;
+  }
+  // empty rows for the new nodes (-1 terminated lists)
+  CUDA_CHECK(cudaMemsetAsync(x->adj0.p + (size_t)n_old * x->slots0, 0xff, (size_t)n_new * x->slots0 * 4, s));
+  if (rows > rows_old)
+    CUDA_CHECK(cudaMemsetAsync(x->adjU.p + (size_t)rows_old * x->slotsU, 0xff, (size_t)(rows - rows_old) * x->slotsU * 4, s));
+  upload_rows(x->vec.p + (size_t)n_old * x->ld, x->ld, data, x->dim, n_new, s);
+  CUDA_CHECK(cudaMemcpyAsync(x->upper_off.p + n_old, uoff_new.data(), (size_t)n_new * 4, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(x->level.p + n_old, lvl_new.data(), (size_t)n_new, cudaMemcpyHostToDevice, s));
+  if (!owner_new.empty())
+    CUDA_CHECK(cudaMemcpyAsync(x->row_owner.p + rows_old, owner_new.data(), owner_new.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  x->h_level.insert(x->h_level.end(), lvl_new.begin(), lvl_new.end());
+  x->h_upper_off.insert(x->h_upper_off.end(), uoff_new.begin(), uoff_new.end());
+  x->h_row_owner.insert(x->h_row_owner.end(), owner_new.begin(), owner_new.end());
+  x->rowsU = rows;
+
+  // scratch
+  BuildPlan bpl = plan_build(x);
+  x->b_ctr.reserve(CTR_N);
+  x->b_counters.reserve(4);
+  x->d_events.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(x->b_counters.p, 0, 4 * sizeof(unsigned long long), s));
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
+  ensure_pool(x, bpl.sp.grid * bpl.sp.warps, n_tot);
+
+  // batch schedule
+  int64_t max_batch = x->param_build_batch > 0 ? x->param_build_batch : 16384;
+  max_batch = std::min<int64_t>(max_batch, (int64_t(1) << hb::REQ_VBITS) - 1);
+  const int64_t ratio = std::max<int64_t>(1, x->param_build_ratio);
+  int64_t done = n_old;
+  if (done == 0) { x->entry = 0; x->max_layer = 0; done = 1; x->n = 1; }     // :774-778
+  while (done < n_tot) {
+    int64_t B = std::max<int64_t>(1, std::min<int64_t>(max_batch, done / ratio));
+    B = std::min<int64_t>(B, n_tot - done);
+    // a node that raises max_layer becomes the entry point (:832-836) and must be seen by
+    // every later insert: it closes its batch
+    for (int64_t j = 0; j < B; j++)
+      if (x->h_level[(size_t)(done + j)] > x->max_layer) { B = j + 1; break; }
+    run_batch(x, bpl, done, B, n_tot);
+    const int64_t last = done + B - 1;
+    if (x->h_level[(size_t)last] > x->max_layer) { x->max_layer = x->h_level[(size_t)last]; x->entry = last; }
+    done += B;
+    x->n = done;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  unsigned long long c[4];
+  CUDA_CHECK(cudaMemcpy(c, x->b_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+  unsigned long long evs[2];
+  CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
+  if (c[3]) fail(HNSWB200_ECUDA, "build: removal buffer overflow");
+  x->st.build_inserts = (uint64_t)n_new;
+  x->st.build_n_dist = c[0];
+  x->st.build_n_exp = c[1];
+  x->st.build_algorithmic_bytes = (double)c[0] * 4.0 * x->dim + (double)c[1] * 4.0 * x->slots0;
+  x->st.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  x->last_nq = 0;
+  x->layer_stats_dirty = true;
+}
+
+}  // namespace
+
 extern "C" {
 
 int hnswb200_build(hnswb200_index* x, const float* data, int64_t n, const int32_t* levels) {
-  return guard([&] { fail(HNSWB200_EINVAL, "build: not implemented yet"); });
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    if (x->n != 0) fail(HNSWB200_EINVAL, "build: the index is not empty (use insert)");
+    x->slots0 = 2 * x->M; x->slotsU = x->M;
+    append_nodes(x, data, n, levels);
+  });
 }
+
 int hnswb200_insert(hnswb200_index* x, const float* data, int64_t n, const int32_t* levels) {
-  return guard([&] { fail(HNSWB200_EINVAL, "insert: not implemented yet"); });
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    append_nodes(x, data, n, levels);
+  });
 }
 
 }  // extern "C"

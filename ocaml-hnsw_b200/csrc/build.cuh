@@ -1,6 +1,380 @@
-// GPU index construction kernels (K3/K4) — see DESIGN.md "Build".
+// GPU index construction: batched restatement of Ohnsw.insert (lib/ohnsw.ml:766-837).
+//
+// The reference inserts one node at a time; every insert sees every earlier one.  Here nodes
+// are inserted in BATCHES against a snapshot of the graph (the host grows the batch with the
+// graph, see api_build.inl), in three deterministic phases per batch:
+//
+//   1. build_search_kernel   one warp per new node: greedy descent (search_one_simple,
+//      :492-508), then for layer = min(level, max_layer) .. 0 the efC beam search seeded with
+//      the whole result set of the layer above (search_k, :543-588, :806-816), the selection
+//      heuristic (select_neighbours, :647-663) and the new node's own adjacency rows
+//      (set_connections_for_new_node, :198-202).  Every selected (row, new node) pair is
+//      emitted as a 64-bit request.
+//   2. requests are radix-sorted by row; build_link_kernel, one warp per distinct row, prepends
+//      the incoming new nodes in id order (what the sequential loop would have done) and, when
+//      the row outgrows its bound (2M on layer 0, M above; :818-823), re-selects it with the
+//      same heuristic keyed on distances to the row's owner (:791-798, :824-826).  Entries that
+//      fall out are emitted as removal requests (the symmetric half of Graph.set_connections,
+//      :182-196).
+//   3. removal requests are sorted by row; build_unlink_kernel, one warp per distinct row,
+//      drops the owners that pruned it.
+//
+// Links stay symmetric after every batch (Graph.Test.invariant, :217-225).  With a batch of
+// one node and the sequential link kernel the phases collapse to the reference's order.
 #pragma once
-#include "common.cuh"
+#include "search.cuh"
 
 namespace hb {
+
+constexpr int REQ_VBITS = 24;            // link request  = row id << 24 | index of the new node in its batch
+constexpr int REM_ABITS = 31;            // unlink request = row id << 31 | owner that dropped the row's node
+constexpr int LINK_MCAP = 96;            // incoming new nodes one row considers per batch
+constexpr uint32_t ROW_UPPER = 0x80000000u;   // row id: node id (layer 0) or ROW_UPPER | upper row index
+
+struct BuildParams {
+  SearchParams sp;          // g = the snapshot (n = nodes already linked), ef = efC
+  int32_t* adj0;            // writable aliases of g.adj0 / g.adjU
+  int32_t* adjU;
+  const int8_t* level;      // [n_total]
+  const int32_t* row_owner; // [rowsU] node that owns each upper row
+  int n0, B;                // this batch = nodes [n0, n0 + B)
+  int sel0, selU;           // neighbours selected for a new node on layer 0 / above (:818)
+  int cap0, capU;           // degree bound of a row before it is re-selected (:822-823)
+  int keep_all;             // Hnsw.Ba shortcut: #candidates <= n keeps all (hnsw_algo.ml:596-599)
+  int sel_cap;              // uint32 slots reserved per warp for the selected list
+  int ucap;                 // link kernel: max union size per row
+  int smem_per_warp;
+  uint64_t* req;            // phase 1 out / phase 2 in (sorted)
+  unsigned int* req_count;
+  uint64_t* rem;            // phase 2 out / phase 3 in (sorted)
+  unsigned int* rem_count;
+  unsigned int rem_cap;
+  const unsigned int* heads;      // segment starts in the sorted request array
+  const unsigned int* head_count;
+  unsigned int n_req;             // number of sorted requests (phase 2 / 3)
+  unsigned int* next;             // work counter
+  unsigned long long* counters;   // [0] distance evaluations, [1] adjacency rows read, [2] dropped incoming, [3] rem overflow
+};
+
+__device__ __forceinline__ int32_t* row_ptr(const BuildParams& bp, uint32_t rid) {
+  return (rid & ROW_UPPER) ? bp.adjU + (size_t)(rid & ~ROW_UPPER) * bp.sp.g.slotsU
+                           : bp.adj0 + (size_t)rid * bp.sp.g.slots0;
+}
+__device__ __forceinline__ uint32_t row_id(const GraphView& g, uint32_t node, int layer) {
+  return layer == 0 ? node : (ROW_UPPER | (uint32_t)(g.upper_off[node] + layer - 1));
+}
+
+// select_neighbours (lib/ohnsw.ml:647-663): candidates ascending by (distance to the base,
+// id); e is kept iff it is strictly closer to the base than to every node already kept.
+// Kept candidates get bit 0 of their key set and are appended to sel[] (oldest first).
+// `qe`/`qs2` receive the candidate's vector.  The kept list is scanned oldest first, eight
+// nodes per round, stopping at the first round that rejects (the reference's for_all scans
+// newest first and stops at the first failure: same verdict, different distance count).
+template <int CPL>
+__device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* cand, int ncand, int want, int keep_all,
+                                                 uint32_t* sel, float4* qe, float4* qs2, float* newd, int lane,
+                                                 uint32_t& n_dist) {
+  int nsel = 0;
+  if (want <= 0) return 0;
+  if (keep_all && ncand <= want) {
+    for (int i = lane; i < ncand; i += 32) { sel[i] = key_id(cand[i]); cand[i] |= 1ull; }
+    __syncwarp();
+    return ncand;
+  }
+  for (int i = 0; i < ncand; i++) {
+    const uint64_t key = cand[i];
+    const uint32_t e = key_id(key);
+    const float de = key_dist(key);
+    bool ok = true;
+    if (nsel > 0) {
+      load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)e * g.ld4, qe, qs2, lane);
+      for (int base = 0; base < nsel; base += 8) {
+        int cnt = min(8, nsel - base);
+        batch_dist<CPL>(g, qe, qs2, sel + base, newd, cnt, lane);
+        n_dist += cnt;
+        bool bad = lane < cnt && !(de < newd[lane]);
+        unsigned any_bad = __ballot_sync(FULL, bad);
+        __syncwarp();
+        if (any_bad) { ok = false; break; }
+      }
+    }
+    if (ok) {
+      if (lane == 0) { sel[nsel] = e; cand[i] = key | 1ull; }
+      nsel++;
+      __syncwarp();
+      if (nsel >= want) break;
+    }
+  }
+  return nsel;
+}
+
+// ---- phase 1 --------------------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SearchParams& p = bp.sp;
+  const GraphView& g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* my = smem_raw + (size_t)warp * bp.smem_per_warp;
+  WarpCtx<CPL> w;
+  w.lane = lane;
+  w.keys = reinterpret_cast<uint64_t*>(my);
+  w.ties = w.keys + p.ef_cap;
+  w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
+  w.newd = reinterpret_cast<float*>(w.newid + 32);
+  w.qs = reinterpret_cast<float4*>(w.newd + 32);
+  w.vis.tab = reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks);
+  w.vis.mask = (uint32_t)p.hash_slots - 1u;
+  w.vis.shift = 32u - (uint32_t)__ffs(p.hash_slots) + 1u;
+  w.vis.limit = (uint32_t)p.hash_slots / 2u + (uint32_t)p.hash_slots / 8u;
+  w.vis.bits = nullptr;
+  w.vis.pool_slot = -1;
+  float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);
+  uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);
+  float4 qe[CPL > 0 ? CPL : 1];
+
+  unsigned long long tot_dist = 0, tot_exp = 0;
+  while (true) {
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(bp.next, 1u);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= (unsigned)bp.B) break;
+    const uint32_t v = (uint32_t)bp.n0 + b;
+    load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)v * g.ld4, w.q, w.qs, lane);
+    const int lv = bp.level[v];
+    uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
+    bool tie_overflow = false;
+
+    // :783-789 entry point, greedy descent through the layers above the node's level
+    uint32_t cur = (uint32_t)g.entry;
+    if (lane == 0) w.newid[0] = cur;
+    __syncwarp();
+    batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, 1, lane);
+    float d_cur = w.newd[0];
+    __syncwarp();
+    for (int layer = g.max_layer; layer > lv; layer--) greedy_layer<CPL>(g, w, layer, cur, d_cur, n_dist, n_expU);
+
+    // :801-802 w_queue = {node}
+    n_dist++;
+    if (lane == 0) w.keys[0] = make_key(d_cur, cur);
+    int n = 1;
+    __syncwarp();
+    for (int layer = min(lv, g.max_layer); layer >= 0; layer--) {       // :806
+      // search_k (:811): the beam is seeded with every element of w_queue, all unexpanded,
+      // all marked visited (:555-557)
+      visited_clear(w.vis, lane);
+      for (int i = lane; i < n; i += 32) {
+        uint64_t k = w.keys[i] & ~1ull;
+        w.keys[i] = k;
+        visited_test_and_set(w.vis, key_id(k));
+      }
+      w.vis.count = n;
+      __syncwarp();
+      layer_search<CPL>(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
+      visited_release(w.vis, p, lane);
+      __syncwarp();
+      // select_neighbours (MinQueue.copy w_queue) nc (:818-819)
+      const int want = layer == 0 ? bp.sel0 : bp.selU;
+      int nsel = select_neighbours<CPL>(g, w.keys, n, want, bp.keep_all, sel, qe, qs2, w.newd, lane, n_dist);
+      // set_connections_for_new_node (:820): Neighbours.add prepends, so the row head is the
+      // last node selected; the reverse half is deferred to the link phase
+      int32_t* row = row_ptr(bp, row_id(g, v, layer));
+      const int slots = layer == 0 ? g.slots0 : g.slotsU;
+      for (int j = lane; j < slots; j += 32) row[j] = j < nsel ? (int32_t)sel[nsel - 1 - j] : -1;
+      unsigned base = 0;
+      if (lane == 0 && nsel) base = atomicAdd(bp.req_count, (unsigned)nsel);
+      base = __shfl_sync(FULL, base, 0);
+      for (int j = lane; j < nsel; j += 32)
+        bp.req[base + j] = ((uint64_t)row_id(g, sel[j], layer) << REQ_VBITS) | (uint64_t)b;
+      __syncwarp();
+    }
+    tot_dist += n_dist;
+    tot_exp += n_exp0 + n_expU;
+    if (tie_overflow && lane == 0) atomicAdd(p.events + 1, 1ull);
+  }
+  if (lane == 0) {
+    atomicAdd(bp.counters + 0, tot_dist);
+    atomicAdd(bp.counters + 1, tot_exp);
+  }
+}
+
+// ---- segment heads of a sorted request array ----------------------------------------------------
+__global__ void segment_heads_kernel(const uint64_t* keys, unsigned n, int shift, unsigned int* heads,
+                                     unsigned int* head_count) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool head = i < n && (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift));
+  unsigned m = __ballot_sync(FULL, head);
+  if (!m) return;
+  int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(head_count, (unsigned)__popc(m));
+  base = __shfl_sync(FULL, base, __ffs(m) - 1);
+  if (head) heads[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+// Rank sort of n distinct keys (shared memory, one warp).
+__device__ __forceinline__ void warp_rank_sort(const uint64_t* in, uint64_t* out, int n, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    uint64_t k = in[i];
+    int r = 0;
+    for (int j = 0; j < n; j++) r += in[j] < k;
+    out[r] = k;
+  }
+  __syncwarp();
+}
+
+// ---- phase 2 --------------------------------------------------------------------------------------
+// Per-warp shared memory: ukey[ucap] u64, sorted[ucap] u64, uid[ucap] u32, ud[ucap] f32,
+// sel[sel_cap] u32, newd[32] f32, qs / qs2.
+__host__ __device__ inline int link_smem_per_warp(int ucap, int sel_cap, int q_chunks) {
+  return ucap * 8 * 2 + ucap * 4 * 2 + sel_cap * 4 + 32 * 4 + 2 * q_chunks * 16;
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GraphView& g = bp.sp.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* my = smem_raw + (size_t)warp * bp.smem_per_warp;
+  uint64_t* ukey = reinterpret_cast<uint64_t*>(my);
+  uint64_t* sorted = ukey + bp.ucap;
+  float4* qs = reinterpret_cast<float4*>(sorted + bp.ucap);
+  float4* qs2 = qs + bp.sp.q_smem_chunks;
+  uint32_t* uid = reinterpret_cast<uint32_t*>(qs2 + bp.sp.q_smem_chunks);
+  float* ud = reinterpret_cast<float*>(uid + bp.ucap);
+  uint32_t* sel = reinterpret_cast<uint32_t*>(ud + bp.ucap);
+  float* newd = reinterpret_cast<float*>(sel + bp.sel_cap);
+  float4 qa[CPL > 0 ? CPL : 1], qe[CPL > 0 ? CPL : 1];
+  const unsigned nheads = *bp.head_count;
+  unsigned long long tot_dist = 0, tot_rows = 0, tot_dropped = 0;
+
+  while (true) {
+    unsigned s = 0;
+    if (lane == 0) s = atomicAdd(bp.next, 1u);
+    s = __shfl_sync(FULL, s, 0);
+    if (s >= nheads) break;
+    const unsigned h = bp.heads[s];
+    const uint64_t k0 = bp.req[h];
+    const uint32_t rid = (uint32_t)(k0 >> REQ_VBITS);
+    // incoming new nodes of this row, ascending id (the order the sequential loop adds them)
+    int m = 0;
+    for (unsigned i = h;; i += 32) {
+      unsigned idx = i + lane;
+      bool in = idx < bp.n_req && (uint32_t)(bp.req[idx] >> REQ_VBITS) == rid;
+      unsigned bm = __ballot_sync(FULL, in);
+      m += __popc(bm);
+      if (bm != FULL) break;
+    }
+    int32_t* row = row_ptr(bp, rid);
+    const bool upper = (rid & ROW_UPPER) != 0;
+    const int slots = upper ? g.slotsU : g.slots0;
+    const int nc = upper ? bp.capU : bp.cap0;
+    uint32_t a;                                       // the row's owner
+    int layer;
+    if (upper) { uint32_t r = rid & ~ROW_UPPER; a = (uint32_t)bp.row_owner[r]; layer = (int)r - g.upper_off[a] + 1; }
+    else { a = rid; layer = 0; }
+    tot_rows++;
+    // union, list order: newest incoming first, then the old row (:116-118 prepend)
+    int dropped_inc = 0;
+    int mm = m;
+    if (mm > LINK_MCAP) { dropped_inc = mm - LINK_MCAP; mm = LINK_MCAP; }   // keeps the LINK_MCAP smallest ids
+    for (int j = lane; j < mm; j += 32)
+      uid[mm - 1 - j] = (uint32_t)bp.n0 + (uint32_t)(bp.req[h + j] & ((1ull << REQ_VBITS) - 1));
+    int deg = 0;
+    for (int r0 = 0; r0 < slots; r0 += 32) {
+      int nb = r0 + lane < slots ? row[r0 + lane] : -1;
+      unsigned bm = __ballot_sync(FULL, nb >= 0);
+      if (nb >= 0) uid[mm + r0 + lane] = (uint32_t)nb;
+      deg += __popc(bm);
+      if (bm != FULL) break;
+    }
+    __syncwarp();
+    const int u = mm + deg;
+    if (u <= nc && dropped_inc == 0) {
+      for (int j = lane; j < u; j += 32) row[j] = (int32_t)uid[j];
+      __syncwarp();
+      continue;
+    }
+    // min_queue_of_neighbours (:791-798): distances from the owner to every member
+    load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)a * g.ld4, qa, qs, lane);
+    batch_dist<CPL>(g, qa, qs, uid, ud, u, lane);
+    uint32_t n_dist = (uint32_t)u;
+    for (int j = lane; j < u; j += 32) ukey[j] = make_key(ud[j], uid[j]);
+    __syncwarp();
+    warp_rank_sort(ukey, sorted, u, lane);
+    int nsel = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist);   // :824-826
+    // Graph.set_connections (:182-196): the row becomes the selected list (head = last kept) ...
+    for (int j = lane; j < slots; j += 32) row[j] = j < nsel ? (int32_t)sel[nsel - 1 - j] : -1;
+    // ... and every member that fell out loses its link to the owner
+    const int nrem = u - nsel + dropped_inc;
+    unsigned base = 0;
+    if (lane == 0 && nrem) base = atomicAdd(bp.rem_count, (unsigned)nrem);
+    base = __shfl_sync(FULL, base, 0);
+    if (nrem && base + (unsigned)nrem > bp.rem_cap) {
+      if (lane == 0) atomicAdd(bp.counters + 3, 1ull);
+    } else if (nrem) {
+      unsigned off = base;
+      for (int j0 = 0; j0 < u; j0 += 32) {
+        int j = j0 + lane;
+        bool out = j < u && !(sorted[j] & 1ull);
+        unsigned bm = __ballot_sync(FULL, out);
+        if (out) {
+          uint32_t x = key_id(sorted[j]);
+          bp.rem[off + __popc(bm & ((1u << lane) - 1u))] = ((uint64_t)row_id(g, x, layer) << REM_ABITS) | (uint64_t)a;
+        }
+        off += __popc(bm);
+      }
+      for (int j = lane; j < dropped_inc; j += 32) {
+        uint32_t x = (uint32_t)bp.n0 + (uint32_t)(bp.req[h + LINK_MCAP + j] & ((1ull << REQ_VBITS) - 1));
+        bp.rem[off + j] = ((uint64_t)row_id(g, x, layer) << REM_ABITS) | (uint64_t)a;
+      }
+    }
+    tot_dist += n_dist;
+    tot_dropped += dropped_inc;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd(bp.counters + 0, tot_dist);
+    atomicAdd(bp.counters + 1, tot_rows);
+    if (tot_dropped) atomicAdd(bp.counters + 2, tot_dropped);
+  }
+}
+
+// ---- phase 3 --------------------------------------------------------------------------------------
+// One warp per row named in the sorted removal requests: drop every owner listed for it.
+__global__ void __launch_bounds__(256) build_unlink_kernel(const BuildParams bp) {
+  const GraphView& g = bp.sp.g;
+  const int lane = threadIdx.x & 31;
+  const unsigned nheads = *bp.head_count;
+  while (true) {
+    unsigned s = 0;
+    if (lane == 0) s = atomicAdd(bp.next, 1u);
+    s = __shfl_sync(FULL, s, 0);
+    if (s >= nheads) break;
+    const unsigned h = bp.heads[s];
+    const uint32_t rid = (uint32_t)(bp.rem[h] >> REM_ABITS);
+    int32_t* row = row_ptr(bp, rid);
+    const int slots = (rid & ROW_UPPER) ? g.slotsU : g.slots0;
+    int out = 0;
+    for (int r0 = 0; r0 < slots; r0 += 32) {
+      int nb = r0 + lane < slots ? row[r0 + lane] : -1;
+      unsigned valid = __ballot_sync(FULL, nb >= 0);
+      bool keep = nb >= 0;
+      for (unsigned i = h; i < bp.n_req; i++) {          // the segment is short (owners that dropped this node)
+        uint64_t k = bp.rem[i];
+        if ((uint32_t)(k >> REM_ABITS) != rid) break;
+        if ((uint32_t)(k & ((1ull << REM_ABITS) - 1)) == (uint32_t)nb) keep = false;
+      }
+      unsigned km = __ballot_sync(FULL, keep);
+      __syncwarp();
+      if (keep) row[out + __popc(km & ((1u << lane) - 1u))] = nb;
+      out += __popc(km);
+      __syncwarp();
+      if (valid != FULL) break;
+    }
+    for (int j = out + lane; j < slots; j += 32) row[j] = -1;
+    __syncwarp();
+  }
+}
+
 }  // namespace hb

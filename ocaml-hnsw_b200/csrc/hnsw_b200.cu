@@ -62,6 +62,8 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = q; n = want;
   }
+  // scratch that grows with the batch: geometric growth, contents dropped
+  void reserve_geo(size_t want) { if (want > n) reserve(std::max(want, n + n / 2)); }
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -82,6 +84,8 @@ struct hnswb200_index {
   DevBuf<float> vec;
   DevBuf<int32_t> adj0, upper_off, adjU;
   DevBuf<int8_t> level;
+  DevBuf<int32_t> row_owner;           // [rowsU] node owning each upper row (build)
+  std::vector<int32_t> h_row_owner;
   std::vector<int8_t> h_level;        // host mirror of level (bookkeeping for build / export)
   std::vector<int32_t> h_upper_off;
   // scratch
@@ -94,6 +98,13 @@ struct hnswb200_index {
   DevBuf<unsigned int> d_next;
   DevBuf<unsigned long long> d_events;
   int pool_size = 0, pool_words = 0;
+  // build scratch
+  DevBuf<uint64_t> b_req, b_req_sorted, b_rem, b_rem_sorted;
+  DevBuf<unsigned int> b_heads, b_ctr;
+  DevBuf<unsigned long long> b_counters;
+  DevBuf<unsigned char> b_cub;
+  int64_t param_build_ratio = 64;
+  bool layer_stats_dirty = true;        // Hgraph.Stats are recomputed only after the graph changed
   int num_sms = 0, max_smem_optin = 0;
   // stats
   hnswb200_stats st{};
@@ -183,8 +194,8 @@ void launch_search(const hb::SearchParams& p, const SearchPlan& pl, cudaStream_t
   CUDA_CHECK(cudaGetLastError());
 }
 
-void ensure_pool(hnswb200_index* x, int total_warps) {
-  int words = (int)((x->n + 31) / 32);
+void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
+  int words = (int)((n_nodes + 31) / 32);
   words = round_up(std::max(words, 1), 4);
   // a spilled query borrows one n-bit set; cap the pool at 1 GiB
   int64_t max_sets = std::max<int64_t>(1, (int64_t(1) << 30) / ((int64_t)words * 4));
@@ -208,7 +219,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   if (ef > 4096) fail(HNSWB200_EINVAL, "search: ef > 4096 is not supported");
   if (nq == 0) return;
   SearchPlan pl = plan_search(x, ef, nq);
-  ensure_pool(x, pl.grid * pl.warps);
+  ensure_pool(x, pl.grid * pl.warps, x->n);
   x->d_counters.reserve((size_t)nq * 3);
   x->d_next.reserve(1);
   x->d_events.reserve(2);
@@ -313,6 +324,8 @@ void import_graph(hnswb200_index* x, const float* data, int64_t n, int id_base, 
   CUDA_CHECK(cudaStreamSynchronize(x->stream));
   x->n = n; x->rowsU = rows; x->max_layer = max_layer; x->entry = entry;
   x->h_level = lvl; x->h_upper_off = uoff;
+  x->h_row_owner.clear(); x->row_owner.release();   // rebuilt on the first insert
+  x->layer_stats_dirty = true;
 }
 
 // host copy of one layer's rows: deg[i], and the row contents
@@ -380,6 +393,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     if (s == "hash_slots") x->param_hash_slots = value;
     else if (s == "build_batch") x->param_build_batch = value;
     else if (s == "warps_per_cta") x->param_warps_per_cta = value;
+    else if (s == "build_ratio") x->param_build_ratio = value;
     else fail(HNSWB200_EINVAL, "unknown parameter: " + s);
   });
 }
@@ -514,9 +528,9 @@ int hnswb200_get_stats(hnswb200_index* x, hnswb200_stats* out) {
     // lib/hnsw.ml:732-751 counts distance calls; bytes per SURVEY.md 8d
     st.search_algorithmic_bytes = (double)st.search_n_dist * 4.0 * x->dim + (double)st.search_n_exp0 * 4.0 * x->slots0 +
                                   (double)st.search_n_expU * 4.0 * x->slotsU;
-    // Hgraph.Stats (lib/hnsw.ml:353-375)
+    // Hgraph.Stats (lib/hnsw.ml:353-375); recomputed only after the graph changed
     st.num_layers = x->n ? x->max_layer + 1 : 0;
-    for (int l = 0; l < st.num_layers && l < 16; l++) {
+    for (int l = 0; x->layer_stats_dirty && l < st.num_layers && l < 16; l++) {
       std::vector<int32_t> rows; int slots = 0;
       download_layer(x, l, rows, slots);
       int64_t nodes = 0, iso = 0, sum = 0; int mn = 1 << 30, mx = -1;
@@ -529,6 +543,7 @@ int hnswb200_get_stats(hnswb200_index* x, hnswb200_stats* out) {
       st.layer_nodes[l] = nodes; st.layer_min_degree[l] = nodes ? mn : 0; st.layer_max_degree[l] = nodes ? mx : 0;
       st.layer_mean_degree[l] = nodes ? (double)sum / (double)nodes : 0.0; st.layer_isolated[l] = iso;
     }
+    x->layer_stats_dirty = false;
     *out = st;
   });
 }

@@ -1,5 +1,6 @@
 // Per-shard top-k merge (K6).  After the all-gather of every shard's `[nq][k]` result rows
-// (ids already global, rows ascending, -1/NaN padded) one warp per query runs an S-way merge:
+// (shard-local ids, made global here by adding the shard's row offset; rows ascending,
+// -1/NaN padded) one warp per query runs an S-way merge:
 // lane s holds the head of shard s's list, the warp minimum of (distance, id) is emitted k
 // times.  80 bytes per query per shard at k = 10 — latency-bound, so it is a single small
 // kernel on the stream right behind the collective.
@@ -8,8 +9,10 @@
 
 namespace hb {
 
+struct ShardOffsets { int32_t v[32]; };   // global id = shard-local id + v[shard]
+
 __global__ void merge_topk_kernel(const int32_t* ids, const float* dists, int S, int64_t nq, int k,
-                                  int32_t* out_ids, float* out_dists) {
+                                  ShardOffsets offs, int32_t* out_ids, float* out_dists) {
   int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (q >= nq) return;
@@ -21,7 +24,7 @@ __global__ void merge_topk_kernel(const int32_t* ids, const float* dists, int S,
     if (lane < S && head < k) {
       int32_t id = ids[base + head];
       myd = dists[base + head];
-      if (id >= 0) key = make_key(myd, (uint32_t)id);
+      if (id >= 0) key = make_key(myd, (uint32_t)(id + offs.v[lane]));
     }
     uint64_t mn = key;
     for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }

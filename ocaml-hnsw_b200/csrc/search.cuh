@@ -190,12 +190,73 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>
   }
 }
 
+
+// target vector -> the team-distributed register copy (CPL > 0) or the shared copy (CPL == 0)
+template <int CPL>
+__device__ __forceinline__ void load_target(const GraphView& g, const float4* row, float4* q, float4* qs, int lane) {
+  const int tl = lane & (TEAM - 1);
+  if (CPL > 0) {
+#pragma unroll
+    for (int c = 0; c < (CPL > 0 ? CPL : 1); c++) {
+      int ch = tl + TEAM * c;
+      q[c] = ch < g.chunks ? __ldg(row + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    __syncwarp();
+    for (int ch = lane; ch < g.chunks; ch += 32) qs[ch] = __ldg(row + ch);
+    __syncwarp();
+  }
+}
+
+// search_one_simple (lib/ohnsw.ml:492-508) on one upper layer: scan the current best's row,
+// move to the row minimum if it is strictly closer, repeat until nothing moves.
+template <int CPL>
+__device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL>& w, int layer, uint32_t& cur,
+                                             float& d_cur, uint32_t& n_dist, uint32_t& n_expU) {
+  const int lane = w.lane;
+  n_dist++;                                       // best_distance = distance (value start) target (:496)
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    int off = g.upper_off[cur];
+    const int32_t* row = off < 0 ? nullptr : g.adjU + ((size_t)off + layer - 1) * g.slotsU;
+    n_expU++;
+    uint64_t best = KEY_INF;                      // (distance, list position) of the running minimum
+    uint32_t best_id = 0;
+    for (int r0 = 0; r0 < g.slotsU && row; r0 += 32) {
+      int nb = (r0 + lane < g.slotsU) ? __ldg(row + r0 + lane) : -1;
+      unsigned m = __ballot_sync(FULL, nb >= 0);
+      int cnt = __popc(m);
+      if (!cnt) break;
+      if (nb >= 0) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
+      __syncwarp();
+      batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);
+      n_dist += cnt;
+      uint64_t mine = lane < cnt ? (((uint64_t)f2ord(w.newd[lane]) << 32) | (uint32_t)(r0 + lane)) : KEY_INF;
+      uint64_t mn = mine;
+      for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }
+      if (mn < best) {
+        best = mn;
+        int src = __ffs(__ballot_sync(FULL, mine == mn)) - 1;
+        best_id = w.newid[src];
+      }
+      __syncwarp();
+      if (m != FULL) break;
+    }
+    // the scan moves `best` on every strictly closer neighbour (:502): it ends on the first
+    // occurrence of the row minimum, if that is strictly closer than the current node
+    if (best != KEY_INF) {
+      float bd = ord2f((uint32_t)(best >> 32));
+      if (bd < d_cur) { d_cur = bd; cur = best_id; changed = true; }
+    }
+  }
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GraphView& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tl = lane & (TEAM - 1);
   unsigned char* my = smem_raw + (size_t)warp * p.smem_per_warp;
   WarpCtx<CPL> w;
   w.lane = lane;
@@ -217,17 +278,8 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= (unsigned)p.nq) break;
 
-    // target -> registers (and shared for the generic path)
-    const float4* qrow = reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4;
-    if (CPL > 0) {
-#pragma unroll
-      for (int c = 0; c < CPL; c++) {
-        int ch = tl + TEAM * c;
-        w.q[c] = ch < g.chunks ? __ldg(qrow + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    } else {
-      for (int ch = lane; ch < g.chunks; ch += 32) w.qs[ch] = __ldg(qrow + ch);
-    }
+    // target -> registers (or shared for the generic path)
+    load_target<CPL>(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.q, w.qs, lane);
     visited_clear(w.vis, lane);
 
     uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
@@ -240,44 +292,7 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, 1, lane);
     float d_cur = w.newd[0];
     __syncwarp();
-    for (int layer = g.max_layer; layer >= 1; layer--) {
-      n_dist++;                                     // best_distance = distance (value start) target (:496)
-      bool changed = true;
-      while (changed) {
-        changed = false;
-        int off = g.upper_off[cur];
-        const int32_t* row = off < 0 ? nullptr : g.adjU + ((size_t)off + layer - 1) * g.slotsU;
-        n_expU++;
-        uint64_t best = KEY_INF;                    // (distance, list position) of the running minimum
-        uint32_t best_id = 0;
-        for (int r0 = 0; r0 < g.slotsU && row; r0 += 32) {
-          int nb = (r0 + lane < g.slotsU) ? __ldg(row + r0 + lane) : -1;
-          unsigned m = __ballot_sync(FULL, nb >= 0);
-          int cnt = __popc(m);
-          if (!cnt) break;
-          if (nb >= 0) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
-          __syncwarp();
-          batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);
-          n_dist += cnt;
-          uint64_t mine = lane < cnt ? (((uint64_t)f2ord(w.newd[lane]) << 32) | (uint32_t)(r0 + lane)) : KEY_INF;
-          uint64_t mn = mine;
-          for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }
-          if (mn < best) {
-            best = mn;
-            int src = __ffs(__ballot_sync(FULL, mine == mn)) - 1;
-            best_id = w.newid[src];
-          }
-          __syncwarp();
-          if (m != FULL) break;
-        }
-        // the scan moves `best` on every strictly closer neighbour (:502): it ends on the first
-        // occurrence of the row minimum, if that is strictly closer than the current node
-        if (best != KEY_INF) {
-          float bd = ord2f((uint32_t)(best >> 32));
-          if (bd < d_cur) { d_cur = bd; cur = best_id; changed = true; }
-        }
-      }
-    }
+    for (int layer = g.max_layer; layer >= 1; layer--) greedy_layer<CPL>(g, w, layer, cur, d_cur, n_dist, n_expU);
 
     // ---- search_k on layer 0 seeded with {node} (:870-873)
     n_dist++;                                       // MinQueue.add_node w_queue !node

@@ -93,6 +93,11 @@ class Hgraph:
         capi.check(capi.lib().hnswb200_export_levels(self._h, capi.ptr(lv)))
         return FlatGraph(inf.n, inf.max_layer, inf.entry_point + id_base, offs, nbrs, lv)
 
+    def search_device(self, d_queries, nq, k, ef, d_ids, d_dists, stream=0, mode=capi.MODE_PARITY):
+        """hnswb200_search_device: all buffers are device pointers (ints) in this index's GPU memory;
+        with a non-zero `stream` (a cudaStream_t) the call only enqueues."""
+        capi.check(capi.lib().hnswb200_search_device(self._h, d_queries, nq, k, ef, mode, d_ids, d_dists, stream or None))
+
     def last_search_counters(self, nq):
         out = np.empty((nq, 3), np.uint32)
         capi.check(capi.lib().hnswb200_last_search_counters(self._h, capi.ptr(out), nq))
@@ -139,15 +144,20 @@ def insert(hgraph, target, *, num_connections=None, num_nodes_search_constructio
     capi.check(capi.lib().hnswb200_insert(hgraph._h, capi.ptr(t), t.shape[0], capi.ptr(lv)))
 
 
-def knn_batch_bigarray(hgraph, batch, *, k, ef=None, mode=capi.MODE_PARITY):
+def knn_batch_bigarray(hgraph, batch, *, k, ef=None, mode=capi.MODE_PARITY, out=None):
     """Ohnsw.knn_batch_bigarray (lib/ohnsw.ml:877-897) -> (ids [nq][k] int32, distances [nq][k] f32).
 
     ids are -1 and distances NaN where fewer than k were found.  The reference's beam width is
     k itself (lib/ohnsw.ml:873); `ef` > k is the "~k:ef, keep the first k rows" use."""
     batch = capi.as_mat(batch, hgraph.dim)
     nq = batch.shape[0]
-    ids = np.empty((nq, k), np.int32)
-    dists = np.empty((nq, k), np.float32)
+    if out is None:
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+    else:                                  # caller-owned result buffers (a Lacaml k x nq mat, pinned or not)
+        ids, dists = out
+        assert ids.shape == (nq, k) and ids.dtype == np.int32 and ids.flags.c_contiguous
+        assert dists.shape == (nq, k) and dists.dtype == np.float32 and dists.flags.c_contiguous
     capi.check(capi.lib().hnswb200_search(hgraph._h, capi.ptr(batch), nq, k, k if ef is None else ef, mode,
                                           capi.ptr(ids), capi.ptr(dists)))
     return ids, dists

@@ -1,0 +1,204 @@
+"""GPU index construction (Ohnsw.build_batch_bigarray / Ohnsw.insert, lib/ohnsw.ml:766-857) vs the
+oracle.  A batched GPU build cannot reproduce the sequential build edge for edge, so parity is:
+
+  * structural invariants the reference's own tests hold (symmetric links, Graph.Test.invariant
+    lib/ohnsw.ml:217-225; degree bounds :818-823; levels and entry point :832-836),
+  * search on the GPU-built graph is id-for-id what the oracle's search returns on the SAME graph
+    (the graph is exported, loaded into the oracle, and both are queried),
+  * recall@10 within 0.005 of an oracle-built index on identical inputs and levels
+    (BASELINE.json north_star), and the reference's distance-threshold recall likewise,
+  * determinism: two builds give the same graph bit for bit.
+
+All calls go through the C ABI."""
+import numpy as np
+import pytest
+
+import ocaml_hnsw_b200 as H
+from ocaml_hnsw_b200 import Hnsw, Ohnsw, capi
+from oracle import oracle as O
+from tests.util import assert_same_results, draw_levels, grid36, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_structure(g, levels, M, cap0=None):
+    cap0 = 2 * M if cap0 is None else cap0
+    n = g.n
+    assert np.array_equal(g.levels, levels)
+    top = int(levels.max())
+    assert g.max_layer == top
+    assert g.entry == int(np.argmax(levels == top))           # first node to reach the top layer (:832-836)
+    for l in range(g.max_layer + 1):
+        deg = g.degree(l)
+        assert deg.max() <= (cap0 if l == 0 else M)
+        assert (deg[levels < l] == 0).all()                   # rows only up to the node's level
+        a = g.nbrs[l]
+        assert a.min() >= 0 and a.max() < n
+        src = np.repeat(np.arange(n), deg)
+        assert (a != src).all(), "self link"
+        pairs = src.astype(np.int64) * n + a
+        assert len(np.unique(pairs)) == len(pairs), "duplicate link"
+        assert np.array_equal(np.sort(pairs), np.sort(a.astype(np.int64) * n + src)), f"layer {l} links are not symmetric"
+
+
+def _to_oracle(X, g, metric=O.METRIC_L2):
+    o = O.VecOracle(X.shape[1], metric)
+    o.import_graph(X, O.Graph(g.n, g.max_layer, g.entry, g.offsets, g.nbrs, g.levels))
+    return o
+
+
+@pytest.fixture(scope="module")
+def built20k():
+    n, M, efC = 20000, 16, 100
+    X = H.sift_like(n, 128, seed=1234)
+    Q = H.sift_like(2000, 128, seed=4321)
+    lv = draw_levels(n, M)
+    h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=M, num_nodes_search_construction=efC, levels=lv)
+    o = O.VecOracle(128).build(X, M, efC, lv)
+    gt_ids, gt_d = H.brute_force_knn_l2(X, Q, 10, return_ids=True)
+    return X, Q, lv, h, o, gt_ids, gt_d
+
+
+def test_structure_and_stats(built20k):
+    X, Q, lv, h, o, _, _ = built20k
+    g = h.export_graph()
+    _check_structure(g, lv, 16)
+    st = h.stats()
+    assert st.build_inserts == len(X) and st.build_n_dist > 0 and st.build_seconds > 0
+    assert st.layer_isolated[0] == 0
+    # same shape of graph as the sequential build: mean layer-0 degree within 10 %
+    go = o.export()
+    dego = np.diff(go.offsets[0])
+    assert abs(g.degree(0).mean() - dego.mean()) < 0.1 * dego.mean()
+
+
+@pytest.mark.parametrize("ef", [10, 32, 64, 128])
+def test_recall_matches_oracle_built_index(built20k, ef):
+    X, Q, lv, h, o, gt_ids, gt_d = built20k
+    ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=ef)
+    ids_o, d_o = o.search_mt(Q, 10, ef)[:2]
+    r_g, r_o = H.Recall.ids(gt_ids, ids_g), H.Recall.ids(gt_ids, ids_o)
+    assert r_g >= r_o - 0.005, f"ef={ef}: GPU-built recall@10 {r_g:.4f} vs oracle-built {r_o:.4f}"
+    # the reference's own recall definition (benchmark/dataset.ml:105-127)
+    c_g, c_o = H.Recall.compute(gt_d, d_g, 1e-4), H.Recall.compute(gt_d, d_o, 1e-4)
+    assert c_g >= c_o - 0.005
+
+
+def test_search_on_gpu_built_graph_is_exact(built20k):
+    X, Q, lv, h, _, _, _ = built20k
+    o2 = _to_oracle(X, h.export_graph())
+    assert o2.invariant()
+    for k, ef in [(10, 10), (10, 64)]:
+        ids_o, d_o, cnt_o = o2.search(Q[:500], k, ef, counters=True)
+        ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q[:500], k=k, ef=ef)
+        assert_same_results(ids_g, d_g, ids_o, d_o)
+        assert np.array_equal(h.last_search_counters(500).astype(np.uint64), cnt_o)
+
+
+def test_build_is_deterministic():
+    X = uniform(6000, 64, 5)
+    lv = draw_levels(len(X), 8)
+    gs = []
+    for _ in range(2):
+        h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=8, num_nodes_search_construction=50, levels=lv)
+        gs.append(h.export_graph())
+    for l in range(gs[0].max_layer + 1):
+        assert np.array_equal(gs[0].offsets[l], gs[1].offsets[l]) and np.array_equal(gs[0].nbrs[l], gs[1].nbrs[l])
+
+
+def test_insert_after_build(built20k):
+    """Ohnsw.insert (lib/ohnsw.ml:766-837) on an existing index, one vector and a batch."""
+    X, Q, lv, _, _, _, _ = built20k
+    n0 = 5000
+    M, efC = 16, 100
+    h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X[:n0], num_connections=M, num_nodes_search_construction=efC, levels=lv[:n0])
+    vis = Ohnsw.Visited.create(n0)
+    Ohnsw.insert(h, X[n0], num_connections=M, num_nodes_search_construction=efC, visited=vis, levels=lv[n0:n0 + 1])
+    assert h.num_nodes() == n0 + 1
+    Ohnsw.insert(h, X[n0 + 1:8000], levels=lv[n0 + 1:8000])
+    assert h.num_nodes() == 8000
+    g = h.export_graph()
+    _check_structure(g, lv[:8000], M)
+    gt, _ = H.brute_force_knn_l2(X[:8000], Q[:500], 10, return_ids=True)
+    ids, _ = Ohnsw.knn_batch_bigarray(h, Q[:500], k=10, ef=64)
+    assert H.Recall.ids(gt, ids) > 0.95
+    with pytest.raises(ValueError):
+        Ohnsw.insert(h, X[0], num_connections=M + 1)
+
+
+def test_insert_into_imported_graph(built20k):
+    """A graph built by the reference/oracle, loaded into the GPU layout, keeps growing on the GPU."""
+    X, Q, lv, _, _, _, _ = built20k
+    n0 = 3000
+    o = O.VecOracle(128).build(X[:n0], 16, 100, lv[:n0])
+    h = Ohnsw.Hgraph(128, Ohnsw.distance_l2, 16, 100).import_graph(X[:n0], o.export())
+    Ohnsw.insert(h, X[n0:6000], levels=lv[n0:6000])
+    g = h.export_graph()
+    _check_structure(g, lv[:6000], 16)
+    gt, _ = H.brute_force_knn_l2(X[:6000], Q[:300], 10, return_ids=True)
+    ids, _ = Ohnsw.knn_batch_bigarray(h, Q[:300], k=10, ef=64)
+    assert H.Recall.ids(gt, ids) > 0.95
+
+
+@pytest.mark.parametrize("n,dim,M,efC,metric", [(1, 8, 4, 10, capi.L2), (2, 8, 4, 10, capi.L2), (37, 3, 3, 20, capi.L2),
+                                                 (3000, 100, 24, 60, capi.ANGULAR), (1500, 960, 16, 60, capi.L2),
+                                                 (4000, 96, 16, 40, capi.L2), (2500, 200, 6, 300, capi.L2)])
+def test_other_shapes(n, dim, M, efC, metric):
+    X = uniform(n, dim, 31)
+    Q = uniform(50, dim, 32)
+    if metric != capi.L2:
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    lv = draw_levels(n, M)
+    lv[0] = 0
+    h = Ohnsw.build_batch_bigarray(metric, X, num_connections=M, num_nodes_search_construction=efC, levels=lv)
+    g = h.export_graph()
+    _check_structure(g, lv, M)
+    o2 = _to_oracle(X, g, {capi.L2: O.METRIC_L2, capi.ANGULAR: O.METRIC_ANGULAR}[metric])
+    k = min(10, n)
+    ids_o, d_o = o2.search(Q, k, 40)
+    ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=k, ef=40)
+    assert_same_results(ids_g, d_g, ids_o, d_o)
+    if n >= 1000:
+        gt, _ = O.bruteforce(X, Q, 10, {capi.L2: O.METRIC_L2, capi.ANGULAR: O.METRIC_ANGULAR}[metric])
+        o = O.VecOracle(dim, {capi.L2: O.METRIC_L2, capi.ANGULAR: O.METRIC_ANGULAR}[metric]).build(X, M, efC, lv)
+        ids_ref, _ = o.search(Q, 10, 40)
+        assert H.Recall.ids(gt, ids_g) >= H.Recall.ids(gt, ids_ref) - 0.03     # 50 queries: loose
+
+
+def test_grid36_build():
+    """test/test.ml:88-127: the 36-point grid, M=3, efC=20, k=3."""
+    X = grid36()
+    lv = draw_levels(36, 3)
+    lv[0] = 0
+    h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=3, num_nodes_search_construction=20, levels=lv)
+    _check_structure(h.export_graph(), lv, 3)
+    ids, d = Ohnsw.knn_batch_bigarray(h, X, k=3)
+    assert (ids[:, 0] == np.arange(36)).mean() > 0.9 and np.allclose(d[ids[:, 0] == np.arange(36), 0], 0)
+
+
+def test_hnsw_ba_flavour_build():
+    """Hnsw.Ba.build / knn_batch (lib/hnsw.ml:753-777): M links per new node, caps 2M / M,
+    distances only, +inf padding."""
+    X = H.sift_like(6000, 128, seed=1)
+    Q = H.sift_like(200, 128, seed=2)
+    lv = draw_levels(len(X), 16)
+    h = Hnsw.Ba.build(X, num_neighbours=16, num_neighbours_build=100, levels=lv)
+    g = h.export_graph()
+    _check_structure(g, lv, 16)
+    d = Hnsw.Ba.knn_batch(h, Q, num_neighbours_search=64, num_neighbours=10)
+    gt = H.brute_force_knn_l2(X, Q, 10)
+    assert H.Recall.compute(gt, d, 1e-4) > 0.95
+    few = Hnsw.Ba.build(X[:4], num_neighbours=4, num_neighbours_build=10, levels=np.zeros(4, np.int32))
+    d = Hnsw.Ba.knn_batch(few, Q[:3], num_neighbours_search=8, num_neighbours=8)
+    assert np.isinf(d[:, 4:]).all() and np.isfinite(d[:, :4]).all()          # lib/hnsw.ml:770-771
+
+
+def test_build_argument_errors():
+    h = Ohnsw.Hgraph(8, Ohnsw.distance_l2, 4, 10)
+    X = uniform(10, 8, 1)
+    with pytest.raises(ValueError, match="level"):
+        capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), 10, capi.ptr(np.full(10, 99, np.int32))))
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), 10, None))
+    with pytest.raises(ValueError, match="not empty"):
+        capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), 10, None))

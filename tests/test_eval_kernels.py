@@ -59,11 +59,12 @@ def test_merge_topk():
     o_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
     o_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
-    capi.check(capi.lib().hnswb200_merge_topk_device(t_ids.data_ptr(), t_d.data_ptr(), S, nq, k,
+    offs = np.arange(S, dtype=np.int64) * (1 << 20)                # shard s holds global rows [s * 2^20, ...)
+    capi.check(capi.lib().hnswb200_merge_topk_device(t_ids.data_ptr(), t_d.data_ptr(), S, nq, k, capi.ptr(offs),
                                                      o_ids.data_ptr(), o_d.data_ptr(), None))
     got_ids, got_d = o_ids.cpu().numpy(), o_d.cpu().numpy()
     for q in range(nq):
-        cand = [(d[s, q, j], ids[s, q, j]) for s in range(S) for j in range(k) if ids[s, q, j] >= 0]
+        cand = [(d[s, q, j], ids[s, q, j] + offs[s]) for s in range(S) for j in range(k) if ids[s, q, j] >= 0]
         cand.sort()
         assert got_ids[q].tolist() == [c[1] for c in cand[:k]]
         assert got_d[q].tolist() == [c[0] for c in cand[:k]]
