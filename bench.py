@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: QPS at recall@10 >= 0.95 on the SIFT-1M shape
+(1M x 128 fp32, L2, 10k queries, M=16, efConstruction=200, k=10),
+plus index build seconds.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA engine
+    python bench.py --impl reference [...]                          # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one batch: a batched k-NN search of all 10k queries
+(Ohnsw.knn_batch_bigarray, lib/ohnsw.ml:877-897) at the smallest ef of the sweep whose recall@10
+is >= 0.95.  The index is built once, on the GPU, before the timed region (build seconds are
+reported beside the QPS).  `value` times the search with queries resident in HBM; `e2e` times the
+public host-buffer call (pinned H2D of the queries + search + D2H of ids and distances).
+
+N > 1 (torchrun, one rank per GPU): the dataset is row-sharded (1M/N rows per GPU), every rank
+searches its shard, one NCCL all-gather + merge kernel per step; `value` = nq / max-over-ranks
+time (total work fixed -> "strong").
+
+Synthetic data: the "SIFT-like" generator of SURVEY.md section 8d(b) (16-d latent, fixed random
+projection to 128-d, noise, integer-valued in [0, 218]); iid-uniform data cannot reach 0.95 at any
+sane ef.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EF_SWEEP = (10, 12, 16, 20, 24, 32, 40, 48, 64, 80, 96, 128, 160, 192, 256, 384, 512)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--M", type=int, default=16)
+    ap.add_argument("--efc", type=int, default=200)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--target-recall", type=float, default=0.95)
+    ap.add_argument("--ref-n", type=int, default=100_000, help="--impl reference: rows the CPU build covers")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"sift-like {a.n}x{a.dim} fp32 L2, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
+
+
+def draw_levels(n, M, seed):
+    """lib/ohnsw.ml:781: round_nearest(-ln U / ln M)."""
+    u = 1.0 - np.random.default_rng(seed).random(n)
+    return np.floor(-np.log(u) / np.log(M) + 0.5).astype(np.int32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = self.proc.communicate()[0]
+        sm, mx, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v == "Active":
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(a):
+    """The reference's own CPU path for this metric.  lehy/ocaml-hnsw is OCaml with un-vendored
+    dependencies and this image has no OCaml toolchain, so the path is the oracle port
+    (oracle/ohnsw_oracle.hpp, a line-by-line restatement of lib/ohnsw.ml).  The sequential CPU build
+    of 1M vectors takes the better part of an hour, so each run builds the index over a bounded
+    prefix of the same dataset (--ref-n rows; a smaller index makes every query cheaper, which
+    favours this arm) and times the batch search of all queries with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ocaml_hnsw_b200.dataset as D           # numpy generators only; no GPU call on this arm
+    from oracle import oracle as O
+    threads = O.lib().orc_num_threads()
+    n = min(a.ref_n, a.n)
+    X = np.ascontiguousarray(D.sift_like(a.n, a.dim, seed=1234)[:n])      # a true prefix of the GPU arm's dataset
+    Q = D.sift_like(a.nq, a.dim, seed=4321)
+    lv = draw_levels(n, a.M, 7)
+    t0 = time.time()
+    o = O.VecOracle(a.dim).build(X, a.M, a.efc, lv)
+    build_s = time.time() - t0
+    gt_n = min(a.nq, 2000)
+    gt, _ = O.bruteforce(X, Q[:gt_n], a.k)
+    ef_star, rec = EF_SWEEP[-1], 0.0
+    for ef in EF_SWEEP:
+        if ef < a.k:
+            continue
+        ids = o.search_mt(Q[:gt_n], a.k, ef)[0]
+        rec = float(np.mean([len(set(g.tolist()) & set(i[i >= 0].tolist())) / a.k for g, i in zip(gt, ids)]))
+        if rec >= a.target_recall:
+            ef_star = ef
+            break
+    for _ in range(a.warmup):
+        o.search_mt(Q, a.k, ef_star)
+    secs = 0.0
+    for _ in range(a.steps):
+        secs += o.search_mt(Q, a.k, ef_star)[2]
+    qps = a.nq * a.steps / secs
+    sample = (f"index built by the CPU port over the first {n} of {a.n} rows (sequential build {build_s:.1f} s), "
+              f"{a.nq} queries/step, ef={ef_star}, recall@{a.k}={rec:.4f} on {gt_n} queries")
+    print(json.dumps({
+        "impl": "reference", "metric": "QPS @ recall@10>=0.95", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": rec, "index_rows": n},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build_seconds": build_s, "gpu_launches": 0}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import ocaml_hnsw_b200 as H
+    from ocaml_hnsw_b200 import Ohnsw, capi
+    from ocaml_hnsw_b200.sharded import ShardedHgraph, gather_rows, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch --gpus N>1 with torchrun (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic inputs (every rank generates the same arrays, then keeps its rows)
+    lo, hi = shard_range(a.n, rank, world)
+    X = H.sift_like(a.n, a.dim, seed=1234)[lo:hi].copy()
+    Q = H.sift_like(a.nq, a.dim, seed=4321)
+    lv = draw_levels(hi - lo, a.M, 7 + rank)
+
+    # ---- index build (outside the timed search region; reported as build seconds)
+    barrier()
+    t0 = time.perf_counter()
+    sh = ShardedHgraph.build(Ohnsw.distance_l2, X, a.n, num_connections=a.M, num_nodes_search_construction=a.efc,
+                             rank=rank, world=world, levels=lv, device=local_rank)
+    torch.cuda.synchronize()
+    build_s = max_over_ranks(time.perf_counter() - t0)
+    h = sh.local
+    bst = h.stats()
+
+    # ---- exact ground truth with the brute-force kernel (per shard, merged like the search results)
+    gt_ids_l, gt_d_l = H.brute_force_knn_l2(X, Q, a.k, device=local_rank, return_ids=True)
+    if world > 1:
+        gi = gather_rows(torch.from_numpy(gt_ids_l).to(dev), world)
+        gd = gather_rows(torch.from_numpy(gt_d_l).to(dev), world)
+        go_i = torch.empty((a.nq, a.k), dtype=torch.int32, device=dev)
+        go_d = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
+        capi.check(capi.lib().hnswb200_merge_topk_device(gi.data_ptr(), gd.data_ptr(), world, a.nq, a.k,
+                                                         capi.ptr(sh.offsets), go_i.data_ptr(), go_d.data_ptr(), None))
+        gt_ids = go_i.cpu().numpy()
+    else:
+        gt_ids = gt_ids_l
+
+    stream = torch.cuda.Stream(device=dev)
+    q_dev = torch.from_numpy(Q).to(dev)
+    torch.cuda.synchronize()
+
+    def search_dev(ef):
+        with torch.cuda.stream(stream):
+            return sh.knn_batch_device(q_dev, k=a.k, ef=ef)
+
+    # ---- ef sweep: smallest ef with recall@10 >= target (setup, untimed)
+    ef_star, rec_star, sweep = None, 0.0, []
+    for ef in EF_SWEEP:
+        if ef < a.k:
+            continue
+        ids, _ = search_dev(ef)
+        stream.synchronize()
+        rec = H.Recall.ids(gt_ids, ids.cpu().numpy())
+        sweep.append((ef, round(rec, 4)))
+        if rec >= a.target_recall:
+            ef_star, rec_star = ef, rec
+            break
+    if ef_star is None:
+        ef_star, rec_star = sweep[-1]
+    # ---- timed region: K search steps, queries resident in HBM
+    for _ in range(a.warmup):
+        search_dev(ef_star)
+    stream.synchronize()
+    launches0 = h.stats().gpu_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(a.steps):
+            sh.knn_batch_device(q_dev, k=a.k, ef=ef_star)
+        e1.record()
+    stream.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = (h.stats().gpu_launches - launches0) + (a.steps if world > 1 else 0)      # + the merge kernel
+    value = a.nq * a.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (search_kernel): algorithmic bytes / CUDA-event duration of the launch
+    kms, abytes = [], 0.0
+    for _ in range(max(3, min(a.steps, 10))):
+        ids, d = Ohnsw.knn_batch_bigarray(h, Q, k=a.k, ef=ef_star)       # own stream: events bracket the kernel alone
+        st = h.stats()
+        kms.append(st.search_kernel_ms)
+        abytes = st.search_algorithmic_bytes + a.nq * (4.0 * a.dim + 8.0 * a.k)
+    peak, peak_src = measured_peak()
+    k_ms = statistics.mean(kms)
+    achieved = abytes / (k_ms * 1e-3) / 1e9
+    st = h.stats()
+
+    # ---- e2e: the public host-buffer call, pinned H2D + D2H inside the timed region
+    Qp = np.ascontiguousarray(Q)
+    out = (np.empty((a.nq, a.k), np.int32), np.empty((a.nq, a.k), np.float32))
+    for buf in (Qp,) + out:
+        capi.host_register(buf)
+    for _ in range(a.warmup):
+        sh.knn_batch_bigarray(Qp, k=a.k, ef=ef_star, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        sh.knn_batch_bigarray(Qp, k=a.k, ef=ef_star, out=out)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_rec = H.Recall.ids(gt_ids, out[0])
+    clocks = sampler.stop() if rank == 0 else None      # covers the value, roofline and e2e loops
+    for buf in (Qp,) + out:
+        capi.host_unregister(buf)
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle port searching the SAME graph
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle as O
+        g = h.export_graph()
+        o = O.VecOracle(a.dim)
+        o.import_graph(X, O.Graph(g.n, g.max_layer, g.entry, g.offsets, g.nbrs, g.levels))
+        threads = O.lib().orc_num_threads()
+        o.search_mt(Q[:1000], a.k, ef_star)
+        reps, secs, ids_o = 0, 0.0, None
+        while secs < 10.0 and reps < 50:
+            ids_o, _, s, _ = o.search_mt(Q, a.k, ef_star)
+            secs += s; reps += 1
+        one = o.search_mt(Q[:2000], a.k, ef_star, nthreads=1)[2]
+        same = bool(np.array_equal(ids_o, out[0]))
+        cpu = {"value": a.nq * reps / secs, "unit": "queries/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port (C++ restatement of lib/ohnsw.ml) searching the same GPU-built graph: {reps} x {a.nq} "
+                         f"queries, ef={ef_star}, {threads} threads; single thread {2000 / one:.0f} queries/s on 2000 queries; "
+                         f"ids identical to the GPU's: {same}"}
+
+    if rank == 0:
+        line = {
+            "metric": "QPS @ recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": round(rec_star, 4), "mode": "parity",
+                       "sharding": f"{world} row shards, all-gather + merge" if world > 1 else "single index",
+                       "l2": "index (vectors + adjacency) larger than L2; no flush between steps",
+                       "ef_sweep": sweep},
+            "build_seconds": build_s,
+            "build": {"inserts_per_s": (hi - lo) / build_s, "dist_evals_per_insert": bst.build_n_dist / max(1, bst.build_inserts),
+                      "library_seconds_rank0": bst.build_seconds},
+            "e2e": {"value": a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(Qp.nbytes),
+                    "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes), "recall_at_10": round(e2e_rec, 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
+                         "dist_evals_per_query": st.search_n_dist / a.nq, "expansions_per_query": st.search_n_exp0 / a.nq},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
