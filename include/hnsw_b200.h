@@ -100,6 +100,7 @@ typedef struct hnswb200_stats {
   int32_t  layer_max_degree[16];
   double   layer_mean_degree[16];
   int64_t  layer_isolated[16];
+  uint64_t build_visited_overflows;  /* inserts whose visited set left shared memory */
 } hnswb200_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

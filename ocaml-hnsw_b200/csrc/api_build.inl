@@ -43,9 +43,10 @@ BuildPlan plan_build(hnswb200_index* x) {
   pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
   pl.ef_cap = round_up(ef, 32);
   int extra = pl.q_chunks * 16 + bp.sel_cap * 4;
-  int hs = x->param_hash_slots > 0 ? next_pow2((int)x->param_hash_slots) : next_pow2(std::max(1024, 32 * ef));
-  hs = std::min(hs, 32768);
-  while (hs > 1024 && hb::search_smem_per_warp(pl.ef_cap, hs, pl.q_chunks) + extra > x->max_smem_optin) hs >>= 1;
+  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 32 * ef), 128);
+  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks) + extra;
+  if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
+  hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
   pl.hash_slots = hs;
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, hs, pl.q_chunks) + extra;
   if (pl.smem_per_warp > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
@@ -284,6 +285,7 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   x->st.build_inserts = (uint64_t)n_new;
   x->st.build_n_dist = c[0];
   x->st.build_n_exp = c[1];
+  x->st.build_visited_overflows = evs[0];
   x->st.build_algorithmic_bytes = (double)c[0] * 4.0 * x->dim + (double)c[1] * 4.0 * x->slots0;
   x->st.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   x->last_nq = 0;

@@ -124,9 +124,8 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   w.newd = reinterpret_cast<float*>(w.newid + 32);
   w.qs = reinterpret_cast<float4*>(w.newd + 32);
   w.vis.tab = reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks);
-  w.vis.mask = (uint32_t)p.hash_slots - 1u;
-  w.vis.shift = 32u - (uint32_t)__ffs(p.hash_slots) + 1u;
-  w.vis.limit = (uint32_t)p.hash_slots / 2u + (uint32_t)p.hash_slots / 8u;
+  w.vis.slots = (uint32_t)p.hash_slots;
+  w.vis.limit = (uint32_t)p.hash_slots / 4u * 3u;
   w.vis.bits = nullptr;
   w.vis.pool_slot = -1;
   float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);

@@ -87,6 +87,7 @@ __device__ __forceinline__ float finish_metric(float acc, int metric) {
   return metric == 0 ? acc : (metric == 1 ? __fsub_rn(1.0f, acc) : -acc);
 }
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Distances from the target (register copy q[CPL] when CPL > 0, shared copy qs otherwise) to
 // two nodes per team (8 vectors per warp), all loads issued before the first use.
@@ -162,27 +163,26 @@ __device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, 
 // Open-addressing hash of id+1 in shared memory; when it would exceed its load bound the set
 // moves to a bitset over all n nodes borrowed from a global pool (exactness is never traded).
 struct VisitedSet {
-  uint32_t* tab;        // shared, `mask+1` slots
-  uint32_t mask;
-  uint32_t shift;
+  uint32_t* tab;        // shared, `slots` slots (a multiple of 4, not necessarily a power of two)
+  uint32_t slots;
   uint32_t limit;       // max entries kept in shared memory
   uint32_t count;       // warp-uniform
   uint32_t* bits;       // non-null once spilled
   int pool_slot;
 };
-__device__ __forceinline__ bool hash_test_and_set(uint32_t* tab, uint32_t mask, uint32_t shift, uint32_t id) {
+__device__ __forceinline__ bool hash_test_and_set(uint32_t* tab, uint32_t slots, uint32_t id) {
   uint32_t key = id + 1u;
-  uint32_t h = (id * 2654435761u) >> shift;
+  uint32_t h = __umulhi(id * 2654435761u, slots);          // multiply-shift range reduction
   while (true) {
     uint32_t old = atomicCAS(&tab[h], 0u, key);
     if (old == 0u) return true;
     if (old == key) return false;
-    h = (h + 1u) & mask;
+    h = h + 1u == slots ? 0u : h + 1u;
   }
 }
 __device__ __forceinline__ void visited_clear(VisitedSet& v, int lane) {
   uint4* t4 = reinterpret_cast<uint4*>(v.tab);
-  for (uint32_t i = lane; i < (v.mask + 1u) / 4u; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = lane; i < v.slots / 4u; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
   v.count = 0;
   __syncwarp();
 }

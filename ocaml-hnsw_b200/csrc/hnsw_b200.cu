@@ -67,7 +67,6 @@ struct DevBuf {
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
-int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 }  // namespace
 
@@ -75,7 +74,7 @@ struct hnswb200_index {
   // configuration
   int dim = 0, metric = 0, M = 0, efC = 0, device = 0, flavour = HNSWB200_FLAVOUR_OHNSW;
   uint64_t seed = 0, rng_state = 0;
-  int64_t param_hash_slots = 0, param_build_batch = 0, param_warps_per_cta = 4;
+  int64_t param_hash_slots = 0, param_build_batch = 0, param_warps_per_cta = 0;
   // graph
   int64_t n = 0, cap = 0;
   int ld = 0, slots0 = 0, slotsU = 0, max_layer = 0;
@@ -165,23 +164,23 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   pl.cpl = cpl <= 4 ? cpl : 0;                        // register-resident query up to 128 dims
   pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
   pl.ef_cap = round_up(ef, 32);
-  int hs = x->param_hash_slots > 0 ? next_pow2((int)x->param_hash_slots) : next_pow2(std::max(1024, 48 * ef));
-  hs = std::min(hs, 32768);
+  // visited hash: ~64 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
+  // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
+  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 64 * ef), 128);
+  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks);
+  if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
+  hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
   pl.hash_slots = hs;
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
-  if (pl.smem_per_warp > x->max_smem_optin) {
-    while (pl.hash_slots > 1024 && hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks) > x->max_smem_optin)
-      pl.hash_slots >>= 1;
-    pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
-    if (pl.smem_per_warp > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
-  }
-  int warps = (int)std::max<int64_t>(1, std::min<int64_t>(x->param_warps_per_cta, 8));
+  // pack the SM: as many warps as shared memory (and ~96 registers per thread) allow, in CTAs of <= 8 warps
+  int per_sm_warps = std::max(1, std::min(20, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 160))));
+  int warps = x->param_warps_per_cta > 0 ? (int)std::min<int64_t>(x->param_warps_per_cta, 8) : 0;
+  if (warps <= 0) { int ctas = (per_sm_warps + 7) / 8; warps = std::max(1, per_sm_warps / ctas); }
   while (warps > 1 && (size_t)warps * pl.smem_per_warp > (size_t)x->max_smem_optin) warps--;
   pl.warps = warps;
   pl.smem = (size_t)warps * pl.smem_per_warp;
-  // persistent grid: as many CTAs as fit per SM (shared memory is the limiter), times the SM count
-  int per_sm = std::max(1, std::min(16, (int)((size_t)(228 * 1024 - 1024) / (pl.smem + 1024))));
-  per_sm = std::min(per_sm, std::max(1, 48 / warps));   // ~48 resident warps is plenty for the gather
+  int per_sm = std::max(1, std::min(16, (int)((size_t)(227 * 1024) / (pl.smem + 1024))));
+  per_sm = std::min(per_sm, std::max(1, (per_sm_warps + warps - 1) / warps));
   int64_t need = (nq + warps - 1) / warps;
   pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * per_sm, need));
   return pl;

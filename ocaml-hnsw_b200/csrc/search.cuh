@@ -22,7 +22,7 @@ struct SearchParams {
   int ef, k, ef_cap;
   int accept_ties;           // Hnsw.Ba flavour: accept d <= top (lib/hnsw.ml:494-506)
   int pad_inf;               // Hnsw.Ba flavour: +inf padding (lib/hnsw.ml:771)
-  int hash_slots;            // power of two
+  int hash_slots;            // multiple of 4
   int q_smem_chunks;         // float4 slots reserved for the query copy
   int smem_per_warp;
   int32_t* out_ids;          // [nq][k] or null
@@ -64,7 +64,7 @@ __device__ __forceinline__ void visited_spill(VisitedSet& v, const SearchParams&
   s = __shfl_sync(FULL, s, 0);
   v.pool_slot = s;
   v.bits = p.bitset_pool + (size_t)s * p.words;
-  for (uint32_t i = lane; i <= v.mask; i += 32) {
+  for (uint32_t i = lane; i < v.slots; i += 32) {
     uint32_t key = v.tab[i];
     if (key) { uint32_t id = key - 1u; atomicOr(&v.bits[id >> 5], 1u << (id & 31)); }
   }
@@ -85,7 +85,7 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id)
     uint32_t bit = 1u << (id & 31);
     return !(atomicOr(&v.bits[id >> 5], bit) & bit);
   }
-  return hash_test_and_set(v.tab, v.mask, v.shift, id);
+  return hash_test_and_set(v.tab, v.slots, id);
 }
 
 // search_k (lib/ohnsw.ml:543-588) on layer `layer`, beam already seeded with `n` keys (all
@@ -105,7 +105,16 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>
       int idx = fu + lane;
       bool un = idx < n && !(w.keys[idx] & 1ull);
       unsigned b = __ballot_sync(FULL, un);
-      if (b) { pos = fu + __ffs(b) - 1; break; }
+      if (b) {
+        pos = fu + __ffs(b) - 1;
+        // the runner-up is the likely next pop: pull its adjacency row towards L2 now
+        unsigned b2 = b & (b - 1u);
+        if (b2 && lane == 0) {
+          uint32_t nx = key_id(w.keys[fu + __ffs(b2) - 1]);
+          if (layer == 0) prefetch_l2(g.adj0 + (size_t)nx * g.slots0);
+        }
+        break;
+      }
       fu += 32;
     }
     if (fu > n) fu = n;
@@ -152,6 +161,12 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>
       if (cnt) {
         if (is_new) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
         __syncwarp();
+        // every vector beyond the first round of eight starts moving towards L2 now, so the
+        // later rounds of batch_dist wait for L2, not for HBM
+        if (lane >= 8 && lane < cnt) {
+          const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[lane] * g.ld4 * 16;
+          for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
+        }
         batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);          // MinQueue.element (:573)
         n_dist += cnt;
         // ---- accept in list order (:574-578)
@@ -266,9 +281,8 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
   w.newd = reinterpret_cast<float*>(w.newid + 32);
   w.qs = reinterpret_cast<float4*>(w.newd + 32);
   w.vis.tab = reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks);
-  w.vis.mask = (uint32_t)p.hash_slots - 1u;
-  w.vis.shift = 32u - (uint32_t)__ffs(p.hash_slots) + 1u;
-  w.vis.limit = (uint32_t)p.hash_slots / 2u + (uint32_t)p.hash_slots / 8u;   // load <= 0.625
+  w.vis.slots = (uint32_t)p.hash_slots;
+  w.vis.limit = (uint32_t)p.hash_slots / 4u * 3u;                            // load <= 0.75
   w.vis.bits = nullptr;
   w.vis.pool_slot = -1;
 

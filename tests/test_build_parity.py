@@ -33,7 +33,7 @@ def _check_structure(g, levels, M, cap0=None):
         assert deg.max() <= (cap0 if l == 0 else M)
         assert (deg[levels < l] == 0).all()                   # rows only up to the node's level
         a = g.nbrs[l]
-        assert a.min() >= 0 and a.max() < n
+        assert len(a) == 0 or (a.min() >= 0 and a.max() < n)
         src = np.repeat(np.arange(n), deg)
         assert (a != src).all(), "self link"
         pairs = src.astype(np.int64) * n + a
