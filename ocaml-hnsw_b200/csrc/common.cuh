@@ -65,19 +65,37 @@ __host__ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return (uint32
 __host__ __device__ __forceinline__ float key_dist(uint64_t k) { return ord2f((uint32_t)(k >> 32)); }
 
 // ---- distance ------------------------------------------------------------------------------------
-__device__ __forceinline__ float acc4(float acc, const float4& a, const float4& b, bool dot) {
+// Packed fp32 pairs (FADD2 / FFMA2 on sm_100a): one instruction per two components, each
+// component rounded exactly like the scalar operation.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rr; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.f32x2 rr, ra, rb; mov.b64 {%0, %1}, rr;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc, rr; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; "
+      "fma.rn.f32x2 rr, ra, rb, rc; mov.b64 {%0, %1}, rr;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// One float4 chunk into the lane's accumulator pair: components x,z feed the first accumulator,
+// y,w the second (the SUM_TEAM8 order of oracle/ohnsw_oracle.hpp).
+__device__ __forceinline__ float2 acc4(float2 acc, const float4& a, const float4& b, bool dot) {
   if (dot) {
-    acc = __fmaf_rn(a.x, b.x, acc); acc = __fmaf_rn(a.y, b.y, acc);
-    acc = __fmaf_rn(a.z, b.z, acc); acc = __fmaf_rn(a.w, b.w, acc);
+    acc = fma2(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+    acc = fma2(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
   } else {
-    float x = __fsub_rn(a.x, b.x); acc = __fmaf_rn(x, x, acc);
-    x = __fsub_rn(a.y, b.y); acc = __fmaf_rn(x, x, acc);
-    x = __fsub_rn(a.z, b.z); acc = __fmaf_rn(x, x, acc);
-    x = __fsub_rn(a.w, b.w); acc = __fmaf_rn(x, x, acc);
+    float2 d = sub2(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    acc = fma2(d, d, acc);
+    d = sub2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    acc = fma2(d, d, acc);
   }
   return acc;
 }
-__device__ __forceinline__ float team_reduce(float acc) {
+__device__ __forceinline__ float team_reduce(float2 acc2) {
+  float acc = __fadd_rn(acc2.x, acc2.y);
   acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 4));
   acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
   acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
@@ -90,71 +108,84 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Distances from the target (register copy q[CPL] when CPL > 0, shared copy qs otherwise) to
-// two nodes per team (8 vectors per warp), all loads issued before the first use.
-// node < 0 = no work for this team.  All 32 lanes must call.
-template <int CPL>
-__device__ __forceinline__ void team_dist2(const GraphView& g, const float4* q, const float4* qs, int node0,
-                                           int node1, int tl, float& out0, float& out1) {
+// NV nodes per team (NV * 4 vectors per warp), all loads issued before the first use.  Every
+// node index must be valid (callers clamp); all 32 lanes must call.  Padding chunks hold zeros
+// in both operands and add exactly +0.
+template <int CPL, int NV>
+__device__ __forceinline__ void team_dist(const GraphView& g, const float4* q, const float4* qs, const int (&node)[NV],
+                                          int tl, float (&out)[NV]) {
   const bool dot = g.metric != 0;
-  float a0 = 0.f, a1 = 0.f;
-  const float4* r0 = reinterpret_cast<const float4*>(g.vec) + (size_t)(node0 < 0 ? 0 : node0) * g.ld4;
-  const float4* r1 = reinterpret_cast<const float4*>(g.vec) + (size_t)(node1 < 0 ? 0 : node1) * g.ld4;
+  float2 acc[NV];
+  const float4* r[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    acc[v] = make_float2(0.f, 0.f);
+    r[v] = reinterpret_cast<const float4*>(g.vec) + (size_t)node[v] * g.ld4;
+  }
   if (CPL > 0) {
-    float4 v0[CPL > 0 ? CPL : 1], v1[CPL > 0 ? CPL : 1];
+    float4 x[NV][CPL > 0 ? CPL : 1];
+    if (g.chunks == TEAM * CPL) {                 // every lane has CPL real chunks (dim 32, 64, 96, 128)
 #pragma unroll
-    for (int c = 0; c < CPL; c++) {
-      int ch = tl + TEAM * c;
-      bool in = ch < g.chunks;
-      v0[c] = (in && node0 >= 0) ? ldg4(r0 + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v1[c] = (in && node1 >= 0) ? ldg4(r1 + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+      for (int c = 0; c < CPL; c++)
 #pragma unroll
-    for (int c = 0; c < CPL; c++) {
-      if (tl + TEAM * c < g.chunks) {      // padding chunks add nothing (keeps -0/+0 exact too)
-        a0 = acc4(a0, q[c], v0[c], dot);
-        a1 = acc4(a1, q[c], v1[c], dot);
+        for (int v = 0; v < NV; v++) x[v][c] = ldg4(r[v] + tl + TEAM * c);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPL; c++) {
+        const bool in = tl + TEAM * c < g.chunks;
+#pragma unroll
+        for (int v = 0; v < NV; v++) x[v][c] = in ? ldg4(r[v] + tl + TEAM * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+#pragma unroll
+    for (int c = 0; c < CPL; c++)
+#pragma unroll
+      for (int v = 0; v < NV; v++) acc[v] = acc4(acc[v], q[c], x[v][c], dot);
   } else {
     for (int ch = tl; ch < g.chunks; ch += 4 * TEAM) {
-      float4 v0[4], v1[4];
+      float4 x[NV][4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        int c = ch + u * TEAM;
-        bool in = c < g.chunks;
-        v0[u] = (in && node0 >= 0) ? ldg4(r0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v1[u] = (in && node1 >= 0) ? ldg4(r1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = ch + u * TEAM;
+#pragma unroll
+        for (int v = 0; v < NV; v++) x[v][u] = c < g.chunks ? ldg4(r[v] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        int c = ch + u * TEAM;
-        if (c < g.chunks) {
-          float4 qq = qs[c];
-          a0 = acc4(a0, qq, v0[u], dot);
-          a1 = acc4(a1, qq, v1[u], dot);
-        }
+        const int c = ch + u * TEAM;
+        const float4 qq = c < g.chunks ? qs[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = acc4(acc[v], qq, x[v][u], dot);
       }
     }
   }
-  out0 = finish_metric(team_reduce(a0), g.metric);
-  out1 = finish_metric(team_reduce(a1), g.metric);
+#pragma unroll
+  for (int v = 0; v < NV; v++) out[v] = finish_metric(team_reduce(acc[v]), g.metric);
 }
 
-// ids[0..cnt) (shared) -> d[0..cnt) (shared).  cnt is warp-uniform.
+// ids[0..cnt) (shared) -> d[0..cnt) (shared).  cnt >= 1 is warp-uniform.  Rounds of eight
+// vectors (two per team) while more than four remain, then one round of up to four.
 template <int CPL>
 __device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, const float4* qs,
                                            const uint32_t* ids, float* d, int cnt, int lane) {
   const int tl = lane & (TEAM - 1), team = lane >> 3;
-  for (int base = 0; base < cnt; base += 8) {
-    int j0 = base + team, j1 = base + 4 + team;
-    int n0 = j0 < cnt ? (int)ids[j0] : -1;
-    int n1 = j1 < cnt ? (int)ids[j1] : -1;
-    float a0, a1;
-    team_dist2<CPL>(g, q, qs, n0, n1, tl, a0, a1);
+  int base = 0;
+  for (; base + 4 < cnt; base += 8) {
+    const int j0 = base + team, j1 = base + 4 + team;
+    const int node[2] = {(int)ids[j0], (int)ids[min(j1, cnt - 1)]};
+    float o[2];
+    team_dist<CPL, 2>(g, q, qs, node, tl, o);
     if (tl == 0) {
-      if (n0 >= 0) d[j0] = a0;
-      if (n1 >= 0) d[j1] = a1;
+      d[j0] = o[0];
+      if (j1 < cnt) d[j1] = o[1];
     }
+  }
+  if (base < cnt) {
+    const int j0 = base + team;
+    const int node[1] = {(int)ids[min(j0, cnt - 1)]};
+    float o[1];
+    team_dist<CPL, 1>(g, q, qs, node, tl, o);
+    if (tl == 0 && j0 < cnt) d[j0] = o[0];
   }
   __syncwarp();
 }

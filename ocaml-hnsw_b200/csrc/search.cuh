@@ -169,35 +169,89 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>
         }
         batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);          // MinQueue.element (:573)
         n_dist += cnt;
-        // ---- accept in list order (:574-578)
-        float t = lane < cnt ? w.newd[lane] : 0.f;
-        uint32_t id = lane < cnt ? w.newid[lane] : 0u;
-        int done = -1;
-        while (true) {
-          bool want = lane < cnt && lane > done &&
-                      (n < ef || (p.accept_ties ? t <= top_d : t < top_d));
-          unsigned wm = __ballot_sync(FULL, want);
-          if (!wm) break;
-          int L = __ffs(wm) - 1;
-          done = L;
-          float tL = __shfl_sync(FULL, t, L);
-          uint32_t idL = __shfl_sync(FULL, id, L);
-          uint64_t ev = beam_insert(w.keys, n, ef, make_key(tL, idL), lane, fu);
-          __syncwarp();
-          if (n == ef) {
-            float new_top = key_dist(w.keys[ef - 1]);
-            if (ev) {                               // Heap.pop_exn nearest_maxq (:577)
-              // the evicted element stays in visit_me; it can still be popped and expanded iff
-              // its distance equals the (new) top (stop rule is a strict >, :568)
-              if (new_top < key_dist(ev)) ties_n = 0;
-              else if (!(ev & 1ull)) {
-                if (ties_n < TIES_CAP) { if (lane == 0) w.ties[ties_n] = ev; ties_n++; }
-                else tie_overflow = true;
+        // ---- accept (:574-578).  The reference takes the candidates one at a time, in list
+        // order: accept iff |near| < ef or t < top (t <= top in the Hnsw.Ba flavour), insert, evict
+        // the maximum.  The same decisions for the whole row at once: with U_j = the beam at the
+        // start of the row plus all earlier candidates, top_j is the ef-th smallest distance of
+        // U_j, so candidate j is accepted iff fewer than ef members of U_j are at distance <= t_j
+        // (< t_j when ties are accepted); the beam after the row is the ef smallest keys of
+        // beam + accepted, and an evicted entry stays poppable only while its distance equals
+        // the top (stop rule is a strict >, :568).
+        const float t = lane < cnt ? w.newd[lane] : 0.f;
+        const uint64_t key = make_key(t, lane < cnt ? w.newid[lane] : 0u);
+        const bool pre = lane < cnt && (n < ef || (p.accept_ties ? t <= top_d : t < top_d));
+        const unsigned pm = __ballot_sync(FULL, pre);
+        if (pm) {
+          int posK = 0;                               // beam keys smaller than mine
+          if (pre) {
+            int lo = 0, hi = n;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (w.keys[mid] < key) lo = mid + 1; else hi = mid; }
+            posK = lo;
+          }
+          bool acc = pre;
+          if (n + __popc(pm) > ef) {
+            int c = posK;                             // beam members at distance <= t (< t with ties)
+            if (pre) {
+              if (p.accept_ties) { while (c > 0 && key_dist(w.keys[c - 1]) == t) c--; }
+              else { while (c < n && key_dist(w.keys[c]) == t) c++; }
+            }
+            for (unsigned m = pm; m; m &= m - 1u) {   // earlier candidates of this row
+              const int i = __ffs(m) - 1;
+              const float ti = __shfl_sync(FULL, t, i);
+              c += (i < lane && (p.accept_ties ? ti < t : ti <= t)) ? 1 : 0;
+            }
+            acc = pre && c < ef;
+          }
+          const unsigned am = __ballot_sync(FULL, acc);
+          if (am) {
+            const bool was_full = n == ef;
+            int rank = 0, minpos = 0x7fffffff;
+            for (unsigned m = am; m; m &= m - 1u) {
+              const int i = __ffs(m) - 1;
+              const uint64_t ki = __shfl_sync(FULL, key, i);
+              const int pi = __shfl_sync(FULL, posK, i);
+              rank += ki < key ? 1 : 0;
+              minpos = min(minpos, pi);
+            }
+            const int f = posK + rank;                // my key's place in the merged order
+            // beam entries move up by the number of accepted keys below them; top chunk first
+            uint64_t ev_key = 0;
+            bool ev = false;
+            for (int base = (n - 1) & ~31; base >= (minpos & ~31); base -= 32) {
+              const int pos = base + lane;
+              const uint64_t kk = pos < n ? w.keys[pos] : 0ull;
+              int sh = 0;
+              for (unsigned m = am; m; m &= m - 1u) sh += __shfl_sync(FULL, posK, __ffs(m) - 1) <= pos ? 1 : 0;
+              __syncwarp();
+              if (pos < n && sh) {
+                if (pos + sh < ef) w.keys[pos + sh] = kk;
+                else { ev = true; ev_key = kk; }
               }
             }
-            top_d = new_top;
+            __syncwarp();
+            if (acc && f < ef) w.keys[f] = key;
+            const int fmin = __reduce_min_sync(FULL, acc ? f : 0x7fffffff);
+            if (fmin < fu) fu = fmin;
+            n = min(ef, n + __popc(am));
+            __syncwarp();
+            if (n == ef) {
+              const float new_top = key_dist(w.keys[ef - 1]);
+              if (was_full && new_top < top_d) ties_n = 0;
+              top_d = new_top;
+              // entries that fell off but tie with the top stay in visit_me (Heap.pop_exn nearest_maxq, :577)
+              const bool t1 = ev && !(ev_key & 1ull) && key_dist(ev_key) == new_top;
+              const bool t2 = acc && f >= ef && t == new_top;
+              const unsigned m1 = __ballot_sync(FULL, t1), m2 = __ballot_sync(FULL, t2);
+              const int c1 = __popc(m1), c2 = __popc(m2);
+              if (ties_n + c1 + c2 > TIES_CAP) tie_overflow = true;
+              else {
+                if (t1) w.ties[ties_n + __popc(m1 & ((1u << lane) - 1u))] = ev_key;
+                if (t2) w.ties[ties_n + c1 + __popc(m2 & ((1u << lane) - 1u))] = key;
+                ties_n += c1 + c2;
+              }
+              __syncwarp();
+            }
           }
-          __syncwarp();
         }
       }
       if (valid != FULL) break;                     // row ended inside this round

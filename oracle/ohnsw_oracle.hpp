@@ -18,12 +18,14 @@
 //     build-dependent (-O3 -ffast-math vectorises it), result widened to double, Float.sqrt
 //     in double.  Two summation orders are offered here:
 //        SUM_SEQUENTIAL : one fp32 accumulator, index order, mul+add   (a scalar Lacaml build)
-//        SUM_TEAM8      : eight fp32 accumulators, accumulator t takes the 4-float chunks
-//                         t, t+8, t+16.. in index order with fused multiply-add, then a
-//                         butterfly (t ^ 4, t ^ 2, t ^ 1).  This is one legal vectorised
-//                         order, and it is the order the CUDA kernels use (8 lanes per
-//                         vector, float4 per lane), which makes GPU-vs-oracle distances
-//                         bit-identical and the id comparison exact.
+//        SUM_TEAM8      : eight accumulator PAIRS; pair t takes the 4-float chunks t, t+8,
+//                         t+16.. in index order, components x and z of each chunk going to
+//                         the first accumulator of the pair, y and w to the second, each with
+//                         a fused multiply-add; the pair is added, then a butterfly
+//                         (t ^ 4, t ^ 2, t ^ 1).  This is one legal vectorised order, and it is
+//                         the order the CUDA kernels use (8 lanes per vector, one float4 per
+//                         lane per step, two packed f32x2 FMAs per float4), which makes
+//                         GPU-vs-oracle distances bit-identical and the id comparison exact.
 //   * TIE ORDER: Core_kernel.Heap (unpinned third party) leaves the order among equal keys
 //     unspecified.  The oracle orders heap elements by the total order (distance, node id);
 //     accept/stop rules still compare distances only, exactly as the reference does.
@@ -160,26 +162,28 @@ inline float team8_butterfly(float* p) {
 }
 // Scalar statement of the TEAM8 order — this is the definition.
 inline float ssqr_diff_team8_scalar(const float* a, const float* b, int d) {
-  float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float pa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, p[8];
   for (int i = 0; i < d; i++) {
     int t = (i >> 2) & 7;
     float x = a[i] - b[i];
-    p[t] = fmaf(x, x, p[t]);
+    if (i & 1) pb[t] = fmaf(x, x, pb[t]); else pa[t] = fmaf(x, x, pa[t]);
   }
+  for (int t = 0; t < 8; t++) p[t] = pa[t] + pb[t];
   return team8_butterfly(p);
 }
 #if defined(__AVX2__) && defined(__FMA__)
 }  // namespace oracle
 #include <immintrin.h>
 namespace oracle {
-// Same arithmetic, eight accumulators in one register.  A block of 32 floats is 8 chunks; a
-// 4x4 transpose inside each 128-bit half gathers component j of the 8 chunks into one
-// register (accumulator order 0,2,4,6,1,3,5,7 inside the register).  Every accumulator still
-// sees its chunks in index order, components x,y,z,w, one fused multiply-add each, so the
-// result is bit-identical to the scalar statement (tests/test_oracle_arith.py checks it).
+// Same arithmetic, the eight first accumulators in one register and the eight second ones in
+// another.  A block of 32 floats is 8 chunks; a 4x4 transpose inside each 128-bit half gathers
+// component j of the 8 chunks into one register (accumulator order 0,2,4,6,1,3,5,7 inside the
+// register).  Every accumulator still sees its chunks in index order, components x,z (first)
+// or y,w (second), one fused multiply-add each, so the result is bit-identical to the scalar
+// statement (tests/test_oracle_arith.py checks it).
 template <bool kDot>
 inline float team8_avx2(const float* a, const float* b, int d) {
-  __m256 P = _mm256_setzero_ps();
+  __m256 PA = _mm256_setzero_ps(), PB = _mm256_setzero_ps();
   int i = 0;
   for (; i + 32 <= d; i += 32) {
     __m256 a0 = _mm256_loadu_ps(a + i), a1 = _mm256_loadu_ps(a + i + 8), a2 = _mm256_loadu_ps(a + i + 16), a3 = _mm256_loadu_ps(a + i + 24);
@@ -196,23 +200,27 @@ inline float team8_avx2(const float* a, const float* b, int d) {
     ORC_T4(a0, a1, a2, a3, ax, ay, az, aw)
     if (kDot) {
       ORC_T4(b0, b1, b2, b3, bx, by, bz, bw)
-      P = _mm256_fmadd_ps(ax, bx, P); P = _mm256_fmadd_ps(ay, by, P);
-      P = _mm256_fmadd_ps(az, bz, P); P = _mm256_fmadd_ps(aw, bw, P);
+      PA = _mm256_fmadd_ps(ax, bx, PA); PB = _mm256_fmadd_ps(ay, by, PB);
+      PA = _mm256_fmadd_ps(az, bz, PA); PB = _mm256_fmadd_ps(aw, bw, PB);
     } else {
-      P = _mm256_fmadd_ps(ax, ax, P); P = _mm256_fmadd_ps(ay, ay, P);
-      P = _mm256_fmadd_ps(az, az, P); P = _mm256_fmadd_ps(aw, aw, P);
+      PA = _mm256_fmadd_ps(ax, ax, PA); PB = _mm256_fmadd_ps(ay, ay, PB);
+      PA = _mm256_fmadd_ps(az, az, PA); PB = _mm256_fmadd_ps(aw, aw, PB);
     }
 #undef ORC_T4
   }
-  float r[8], p[8];
-  _mm256_storeu_ps(r, P);
+  float ra[8], rb[8], pa[8], pb[8], p[8];
+  _mm256_storeu_ps(ra, PA);
+  _mm256_storeu_ps(rb, PB);
   // register slot s holds accumulator: low half chunks 0,2,4,6 ; high half chunks 1,3,5,7
-  p[0] = r[0]; p[2] = r[1]; p[4] = r[2]; p[6] = r[3]; p[1] = r[4]; p[3] = r[5]; p[5] = r[6]; p[7] = r[7];
+  static const int slot[8] = {0, 2, 4, 6, 1, 3, 5, 7};
+  for (int s = 0; s < 8; s++) { pa[slot[s]] = ra[s]; pb[slot[s]] = rb[s]; }
   for (; i < d; i++) {
     int t = (i >> 2) & 7;
-    if (kDot) p[t] = fmaf(a[i], b[i], p[t]);
-    else { float x = a[i] - b[i]; p[t] = fmaf(x, x, p[t]); }
+    float* acc = (i & 1) ? pb : pa;
+    if (kDot) acc[t] = fmaf(a[i], b[i], acc[t]);
+    else { float x = a[i] - b[i]; acc[t] = fmaf(x, x, acc[t]); }
   }
+  for (int t = 0; t < 8; t++) p[t] = pa[t] + pb[t];
   return team8_butterfly(p);
 }
 inline float ssqr_diff_team8(const float* a, const float* b, int d) { return team8_avx2<false>(a, b, d); }
@@ -225,8 +233,12 @@ inline float dot_sequential(const float* a, const float* b, int d) {
   return acc;
 }
 inline float dot_team8_scalar(const float* a, const float* b, int d) {
-  float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < d; i++) { int t = (i >> 2) & 7; p[t] = fmaf(a[i], b[i], p[t]); }
+  float pa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, p[8];
+  for (int i = 0; i < d; i++) {
+    int t = (i >> 2) & 7;
+    if (i & 1) pb[t] = fmaf(a[i], b[i], pb[t]); else pa[t] = fmaf(a[i], b[i], pa[t]);
+  }
+  for (int t = 0; t < 8; t++) p[t] = pa[t] + pb[t];
   return team8_butterfly(p);
 }
 #if defined(__AVX2__) && defined(__FMA__)

@@ -15,7 +15,7 @@ def _team8_numpy(a, b, dot=False):
     of two fp32 is exact in fp64 and one fp64 add of an fp32 is rounded once more to fp32 —
     double rounding can differ from a true fma only when the fp64 sum is a tie, which the
     comparison below tolerates by falling back to the C scalar definition)."""
-    p = np.zeros(8, np.float32)
+    pp = np.zeros((2, 8), np.float32)          # accumulator pairs: components x,z -> [0], y,w -> [1]
     for i in range(len(a)):
         t = (i >> 2) & 7
         if dot:
@@ -23,7 +23,8 @@ def _team8_numpy(a, b, dot=False):
         else:
             x = np.float32(a[i] - b[i])
             prod = np.float64(x) * np.float64(x)
-        p[t] = np.float32(prod + np.float64(p[t]))
+        pp[i & 1, t] = np.float32(prod + np.float64(pp[i & 1, t]))
+    p = (pp[0] + pp[1]).astype(np.float32)
     for m in (4, 2, 1):
         p = np.array([np.float32(p[t] + p[t ^ m]) for t in range(8)], np.float32)
     return float(p[0])
