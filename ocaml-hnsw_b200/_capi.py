@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhnsw_b200.so")
+LIB_PATH = os.environ.get("HNSWB200_LIB") or os.path.join(_HERE, "libhnsw_b200.so")   # env override: kernel tuning builds only
 
 OK, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3
 L2, ANGULAR, IP = 0, 1, 2

@@ -24,7 +24,7 @@ struct BuildPlan {
   int sel0, selU, cap0, capU, keep_all;
 };
 
-BuildPlan plan_build(hnswb200_index* x) {
+BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   BuildPlan bp;
   const bool ba = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   bp.sel0 = ba ? x->M : 2 * x->M;              // lib/ohnsw.ml:818 vs lib/hnsw.ml:753-758 (Q3)
@@ -47,6 +47,9 @@ BuildPlan plan_build(hnswb200_index* x) {
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks) + extra;
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
   hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
+  if (x->param_visited_mode != 1 && x->param_hash_slots == 0 && fixed + hs * 4 > 14 * 1024 &&
+      (double)n_total / 8.0 <= 0.3 * 26.0 * ef * 4.0 * x->dim) hs = 0;      // see use_bitset_visited
+  if (x->param_visited_mode == 2) hs = 0;
   pl.hash_slots = hs;
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, hs, pl.q_chunks) + extra;
   if (pl.smem_per_warp > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
@@ -249,13 +252,14 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   x->rowsU = rows;
 
   // scratch
-  BuildPlan bpl = plan_build(x);
+  BuildPlan bpl = plan_build(x, n_tot);
   x->b_ctr.reserve(CTR_N);
   x->b_counters.reserve(4);
   x->d_events.reserve(2);
   CUDA_CHECK(cudaMemsetAsync(x->b_counters.p, 0, 4 * sizeof(unsigned long long), s));
   CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
   ensure_pool(x, bpl.sp.grid * bpl.sp.warps, n_tot);
+  if (bpl.sp.hash_slots == 0) bpl.sp.grid = std::max(1, std::min(bpl.sp.grid, x->pool_size / bpl.sp.warps));   // one set per warp
 
   // batch schedule
   int64_t max_batch = x->param_build_batch > 0 ? x->param_build_batch : 16384;

@@ -123,11 +123,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
   w.newd = reinterpret_cast<float*>(w.newid + 32);
   w.qs = reinterpret_cast<float4*>(w.newd + 32);
-  w.vis.tab = reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks);
-  w.vis.slots = (uint32_t)p.hash_slots;
-  w.vis.limit = (uint32_t)p.hash_slots / 4u * 3u;
-  w.vis.bits = nullptr;
-  w.vis.pool_slot = -1;
+  visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
   float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);
   uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);
   float4 qe[CPL > 0 ? CPL : 1];
@@ -148,10 +144,10 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     uint32_t cur = (uint32_t)g.entry;
     if (lane == 0) w.newid[0] = cur;
     __syncwarp();
-    batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, 1, lane);
+    batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, 1, lane);
     float d_cur = w.newd[0];
     __syncwarp();
-    for (int layer = g.max_layer; layer > lv; layer--) greedy_layer<CPL>(g, w, layer, cur, d_cur, n_dist, n_expU);
+    for (int layer = g.max_layer; layer > lv; layer--) greedy_layer(g, w, layer, cur, d_cur, n_dist, n_expU);
 
     // :801-802 w_queue = {node}
     n_dist++;
@@ -169,7 +165,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
       }
       w.vis.count = n;
       __syncwarp();
-      layer_search<CPL>(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
+      layer_search(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
       visited_release(w.vis, p, lane);
       __syncwarp();
       // select_neighbours (MinQueue.copy w_queue) nc (:818-819)

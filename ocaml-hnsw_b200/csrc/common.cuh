@@ -137,10 +137,14 @@ __device__ __forceinline__ void team_dist(const GraphView& g, const float4* q, c
         for (int v = 0; v < NV; v++) x[v][c] = in ? ldg4(r[v] + tl + TEAM * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    // q == nullptr (a literal at the call site): the target stays in shared memory, padded with
+    // zero chunks to TEAM * CPL, and is read chunk by chunk — 4 * CPL fewer live registers
 #pragma unroll
-    for (int c = 0; c < CPL; c++)
+    for (int c = 0; c < CPL; c++) {
+      const float4 qq = q ? q[c] : qs[tl + TEAM * c];
 #pragma unroll
-      for (int v = 0; v < NV; v++) acc[v] = acc4(acc[v], q[c], x[v][c], dot);
+      for (int v = 0; v < NV; v++) acc[v] = acc4(acc[v], qq, x[v][c], dot);
+    }
   } else {
     for (int ch = tl; ch < g.chunks; ch += 4 * TEAM) {
       float4 x[NV][4];

@@ -102,7 +102,7 @@ struct hnswb200_index {
   DevBuf<unsigned int> b_heads, b_ctr;
   DevBuf<unsigned long long> b_counters;
   DevBuf<unsigned char> b_cub;
-  int64_t param_build_ratio = 64;
+  int64_t param_build_ratio = 64, param_max_warps_per_sm = 0, param_visited_mode = 0;   // 0 auto, 1 hash, 2 bitset
   bool layer_stats_dirty = true;        // Hgraph.Stats are recomputed only after the graph changed
   int num_sms = 0, max_smem_optin = 0;
   // stats
@@ -157,25 +157,48 @@ struct SearchPlan {
   size_t smem;
 };
 
+// Visited set of a query: exact open-addressing hash in shared memory, or one n-bit set per warp
+// in global memory.  The hash costs shared memory (fewer resident warps: throughput is linear in
+// resident warps up to ~24 per SM); the bitset costs one global atomic round trip per expansion
+// and an n/8-byte clear per query.  Bitset when the hash would leave fewer than 24 warps per SM
+// and the clear is small next to the vectors the query reads (~26 * ef of them).
+bool use_bitset_visited(const hnswb200_index* x, int ef, int smem_per_warp_hash, int64_t n_nodes) {
+  if (x->param_visited_mode == 1) return false;
+  if (x->param_visited_mode == 2) return true;
+  if (x->param_hash_slots > 0) return false;
+  const double clear_bytes = (double)n_nodes / 8.0, query_bytes = 26.0 * ef * 4.0 * x->dim;
+  return smem_per_warp_hash > (227 * 1024) / (4 * HB_SEARCH_MINB) - 256 && clear_bytes <= 0.3 * query_bytes;
+}
+
 SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   SearchPlan pl;
   int chunks = x->ld / 4;
   int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
   pl.cpl = cpl <= 4 ? cpl : 0;                        // register-resident query up to 128 dims
-  pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
+  pl.q_chunks = pl.cpl ? hb::TEAM * pl.cpl : round_up(chunks, 2);   // the target lives in shared memory
   pl.ef_cap = round_up(ef, 32);
-  // visited hash: ~64 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
+  // visited hash: ~42 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
-  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 64 * ef), 128);
+  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 42 * ef), 128);
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks);
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
   hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
+  if (use_bitset_visited(x, ef, fixed + hs * 4, x->n)) hs = 0;
   pl.hash_slots = hs;
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
-  // pack the SM: as many warps as shared memory (and ~96 registers per thread) allow, in CTAs of <= 8 warps
-  int per_sm_warps = std::max(1, std::min(20, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 160))));
-  int warps = x->param_warps_per_cta > 0 ? (int)std::min<int64_t>(x->param_warps_per_cta, 8) : 0;
-  if (warps <= 0) { int ctas = (per_sm_warps + 7) / 8; warps = std::max(1, per_sm_warps / ctas); }
+  // pack the SM: as many warps as shared memory and registers (64 per thread: 32 warps) allow, in CTAs of <= 4 warps
+  int per_sm_warps = std::max(1, std::min(4 * HB_SEARCH_MINB, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 256))));
+  if (x->param_max_warps_per_sm > 0) per_sm_warps = std::max(1, std::min<int>(per_sm_warps, (int)x->param_max_warps_per_sm));
+  int warps = x->param_warps_per_cta > 0 ? (int)std::min<int64_t>(x->param_warps_per_cta, 4) : 0;
+  if (warps <= 0) {                                   // CTA shape that keeps the most warps resident (1 KB reserved per CTA)
+    int best = 0;
+    for (int w = 4; w >= 1; w--) {
+      int ctas = (int)((size_t)(227 * 1024) / ((size_t)w * pl.smem_per_warp + 1024));
+      int tot = std::min(per_sm_warps / w, ctas) * w;
+      if (tot > best) { best = tot; warps = w; }
+    }
+    warps = std::max(1, warps);
+  }
   while (warps > 1 && (size_t)warps * pl.smem_per_warp > (size_t)x->max_smem_optin) warps--;
   pl.warps = warps;
   pl.smem = (size_t)warps * pl.smem_per_warp;
@@ -196,8 +219,8 @@ void launch_search(const hb::SearchParams& p, const SearchPlan& pl, cudaStream_t
 void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
   int words = (int)((n_nodes + 31) / 32);
   words = round_up(std::max(words, 1), 4);
-  // a spilled query borrows one n-bit set; cap the pool at 1 GiB
-  int64_t max_sets = std::max<int64_t>(1, (int64_t(1) << 30) / ((int64_t)words * 4));
+  // a spilled query (or, for large beams, every warp) borrows one n-bit set; cap the pool at 4 GiB
+  int64_t max_sets = std::max<int64_t>(1, (int64_t(4) << 30) / ((int64_t)words * 4));
   int want = (int)std::min<int64_t>(total_warps, max_sets);
   if (want > x->pool_size || words > x->pool_words) {
     x->d_bitpool.release();
@@ -219,6 +242,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   if (nq == 0) return;
   SearchPlan pl = plan_search(x, ef, nq);
   ensure_pool(x, pl.grid * pl.warps, x->n);
+  if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));   // one set per warp
   x->d_counters.reserve((size_t)nq * 3);
   x->d_next.reserve(1);
   x->d_events.reserve(2);
@@ -393,6 +417,8 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "build_batch") x->param_build_batch = value;
     else if (s == "warps_per_cta") x->param_warps_per_cta = value;
     else if (s == "build_ratio") x->param_build_ratio = value;
+    else if (s == "max_warps_per_sm") x->param_max_warps_per_sm = value;
+    else if (s == "visited_mode") x->param_visited_mode = value;
     else fail(HNSWB200_EINVAL, "unknown parameter: " + s);
   });
 }

@@ -13,6 +13,15 @@
 #pragma once
 #include "common.cuh"
 
+// Tuning knobs of search_kernel (measured on B200): minimum resident CTAs of 128
+// threads per SM (register budget = 65536 / (128 * MINB)) and where the target vector lives.
+#ifndef HB_SEARCH_MINB
+#define HB_SEARCH_MINB 6
+#endif
+#ifndef HB_SEARCH_QREG
+#define HB_SEARCH_QREG false
+#endif
+
 namespace hb {
 
 struct SearchParams {
@@ -40,16 +49,19 @@ __host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, 
   return ef_cap * 8 + TIES_CAP * 8 + 32 * 4 + 32 * 4 + q_chunks * 16 + hash_slots * 4;
 }
 
-template <int CPL>
+// QREG: the target vector lives in registers (CPL float4 per lane); otherwise in shared memory
+// (qs, zero padded to TEAM * CPL chunks) — fewer live registers, more resident warps.
+template <int CPL, bool QREG = true>
 struct WarpCtx {
   uint64_t* keys;
   uint64_t* ties;
   uint32_t* newid;
   float* newd;
   float4* qs;
-  float4 q[CPL > 0 ? CPL : 1];
+  float4 q[(CPL > 0 && QREG) ? CPL : 1];
   VisitedSet vis;
   int lane;
+  __device__ __forceinline__ const float4* target_regs() const { return (CPL > 0 && QREG) ? q : nullptr; }
 };
 
 __device__ __forceinline__ void visited_spill(VisitedSet& v, const SearchParams& p, int lane) {
@@ -72,11 +84,27 @@ __device__ __forceinline__ void visited_spill(VisitedSet& v, const SearchParams&
 }
 __device__ __forceinline__ void visited_release(VisitedSet& v, const SearchParams& p, int lane) {
   if (v.bits) {
-    for (int i = lane; i < p.words; i += 32) v.bits[i] = 0u;
+    uint4* b4 = reinterpret_cast<uint4*>(v.bits);
+    for (int i = lane; i < p.words / 4; i += 32) b4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
+    if (v.slots == 0u) return;                 // bitset is this warp's primary set: it keeps its slot
     __threadfence();
     if (lane == 0) atomicExch(&p.pool_busy[v.pool_slot], 0);
     v.bits = nullptr;
+  }
+}
+// Large beams: the visited set of a query would not leave room for enough resident warps in
+// shared memory, so every warp owns one n-bit set of the global pool for its whole life.
+__device__ __forceinline__ void visited_init(VisitedSet& v, const SearchParams& p, uint32_t* tab) {
+  v.tab = tab;
+  v.slots = (uint32_t)p.hash_slots;
+  v.limit = (uint32_t)p.hash_slots / 4u * 3u;                                // load <= 0.75
+  v.bits = nullptr;
+  v.pool_slot = -1;
+  if (p.hash_slots == 0) {
+    v.pool_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);        // host guarantees pool_size >= warps
+    v.bits = p.bitset_pool + (size_t)v.pool_slot * p.words;
+    v.limit = 0xffffffffu;
   }
 }
 // true if `id` was not yet visited (and marks it).  Called by a subset of lanes.
@@ -90,8 +118,8 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id)
 
 // search_k (lib/ohnsw.ml:543-588) on layer `layer`, beam already seeded with `n` keys (all
 // unexpanded, all marked visited).  Leaves the nearest set in keys[0..n).
-template <int CPL>
-__device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>& w, int layer, int& n,
+template <int CPL, bool QREG>
+__device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL, QREG>& w, int layer, int& n,
                                              uint32_t& n_dist, uint32_t& n_exp, bool& tie_overflow) {
   const GraphView& g = p.g;
   const int lane = w.lane;
@@ -167,7 +195,7 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL>
           const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[lane] * g.ld4 * 16;
           for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
         }
-        batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);          // MinQueue.element (:573)
+        batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, cnt, lane);          // MinQueue.element (:573)
         n_dist += cnt;
         // ---- accept (:574-578).  The reference takes the candidates one at a time, in list
         // order: accept iff |near| < ef or t < top (t <= top in the Hnsw.Ba flavour), insert, evict
@@ -277,10 +305,17 @@ __device__ __forceinline__ void load_target(const GraphView& g, const float4* ro
   }
 }
 
+// target vector -> shared memory, zero padded to `padded` chunks (the register-free variant)
+__device__ __forceinline__ void load_target_smem(const GraphView& g, const float4* row, float4* qs, int padded, int lane) {
+  __syncwarp();
+  for (int ch = lane; ch < padded; ch += 32) qs[ch] = ch < g.chunks ? __ldg(row + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+}
+
 // search_one_simple (lib/ohnsw.ml:492-508) on one upper layer: scan the current best's row,
 // move to the row minimum if it is strictly closer, repeat until nothing moves.
-template <int CPL>
-__device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL>& w, int layer, uint32_t& cur,
+template <int CPL, bool QREG>
+__device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL, QREG>& w, int layer, uint32_t& cur,
                                              float& d_cur, uint32_t& n_dist, uint32_t& n_expU) {
   const int lane = w.lane;
   n_dist++;                                       // best_distance = distance (value start) target (:496)
@@ -299,7 +334,7 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL>& w
       if (!cnt) break;
       if (nb >= 0) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
       __syncwarp();
-      batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, cnt, lane);
+      batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, cnt, lane);
       n_dist += cnt;
       uint64_t mine = lane < cnt ? (((uint64_t)f2ord(w.newd[lane]) << 32) | (uint32_t)(r0 + lane)) : KEY_INF;
       uint64_t mn = mine;
@@ -322,23 +357,19 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL>& w
 }
 
 template <int CPL>
-__global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GraphView& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* my = smem_raw + (size_t)warp * p.smem_per_warp;
-  WarpCtx<CPL> w;
+  WarpCtx<CPL, HB_SEARCH_QREG> w;
   w.lane = lane;
   w.keys = reinterpret_cast<uint64_t*>(my);
   w.ties = w.keys + p.ef_cap;
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
   w.newd = reinterpret_cast<float*>(w.newid + 32);
   w.qs = reinterpret_cast<float4*>(w.newd + 32);
-  w.vis.tab = reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks);
-  w.vis.slots = (uint32_t)p.hash_slots;
-  w.vis.limit = (uint32_t)p.hash_slots / 4u * 3u;                            // load <= 0.75
-  w.vis.bits = nullptr;
-  w.vis.pool_slot = -1;
+  visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
 
   while (true) {
     unsigned qi = 0;
@@ -347,7 +378,8 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     if (qi >= (unsigned)p.nq) break;
 
     // target -> registers (or shared for the generic path)
-    load_target<CPL>(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.q, w.qs, lane);
+    if (HB_SEARCH_QREG) load_target<CPL>(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.q, w.qs, lane);
+    else load_target_smem(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.qs, p.q_smem_chunks, lane);
     visited_clear(w.vis, lane);
 
     uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
@@ -357,10 +389,10 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     uint32_t cur = (uint32_t)g.entry;
     if (lane == 0) w.newid[0] = cur;
     __syncwarp();
-    batch_dist<CPL>(g, w.q, w.qs, w.newid, w.newd, 1, lane);
+    batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, 1, lane);
     float d_cur = w.newd[0];
     __syncwarp();
-    for (int layer = g.max_layer; layer >= 1; layer--) greedy_layer<CPL>(g, w, layer, cur, d_cur, n_dist, n_expU);
+    for (int layer = g.max_layer; layer >= 1; layer--) greedy_layer(g, w, layer, cur, d_cur, n_dist, n_expU);
 
     // ---- search_k on layer 0 seeded with {node} (:870-873)
     n_dist++;                                       // MinQueue.add_node w_queue !node
@@ -369,7 +401,7 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     visited_test_and_set(w.vis, lane == 0 ? cur : cur);   // all lanes race on the same slot: one wins
     w.vis.count = 1;
     __syncwarp();
-    layer_search<CPL>(p, w, 0, n, n_dist, n_exp0, tie_overflow);
+    layer_search(p, w, 0, n, n_dist, n_exp0, tie_overflow);
 
     // ---- pop ascending into the result rows (:886-893)
     for (int i = lane; i < p.k; i += 32) {

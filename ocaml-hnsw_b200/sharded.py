@@ -32,7 +32,8 @@ def gather_rows(local, world, group=None):
     if world == 1:
         out[0].copy_(local)
     else:
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        # concatenated along dim 0 (the layout every backend accepts); `out` is the stacked view of it
+        dist.all_gather_into_tensor(out.view((world * local.shape[0],) + tuple(local.shape[1:])), local.contiguous(), group=group)
     return out
 
 
