@@ -18,6 +18,33 @@ int draw_level(hnswb200_index* x) {
   return (int)std::floor(-std::log(u) * mL + 0.5);
 }
 
+// resident CTAs per SM of a persistent kernel (registers and shared memory both count)
+template <class K>
+int resident_ctas(K kernel, int threads, size_t smem) {
+  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int nb = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
+  return std::max(1, nb);
+}
+int build_search_resident(int cpl, int threads, size_t smem) {
+  switch (cpl) {
+    case 1: return resident_ctas(hb::build_search_kernel<1>, threads, smem);
+    case 2: return resident_ctas(hb::build_search_kernel<2>, threads, smem);
+    case 3: return resident_ctas(hb::build_search_kernel<3>, threads, smem);
+    case 4: return resident_ctas(hb::build_search_kernel<4>, threads, smem);
+    default: return resident_ctas(hb::build_search_kernel<0>, threads, smem);
+  }
+}
+int build_link_resident(int cpl, int threads, size_t smem) {
+  switch (cpl) {
+    case 1: return resident_ctas(hb::build_link_kernel<1>, threads, smem);
+    case 2: return resident_ctas(hb::build_link_kernel<2>, threads, smem);
+    case 3: return resident_ctas(hb::build_link_kernel<3>, threads, smem);
+    case 4: return resident_ctas(hb::build_link_kernel<4>, threads, smem);
+    default: return resident_ctas(hb::build_link_kernel<0>, threads, smem);
+  }
+}
+
 struct BuildPlan {
   SearchPlan sp;
   int sel_cap, ucap, link_warps, link_smem_per_warp, link_grid_per_sm;
@@ -59,13 +86,13 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   pl.warps = std::max(1, per_sm_warps / ctas);
   while (pl.warps > 1 && (size_t)pl.warps * pl.smem_per_warp > (size_t)x->max_smem_optin) pl.warps--;
   pl.smem = (size_t)pl.warps * pl.smem_per_warp;
-  pl.grid = x->num_sms * std::max(1, (int)((size_t)(227 * 1024) / (pl.smem + 1024)));
+  pl.grid = x->num_sms * build_search_resident(pl.cpl, pl.warps * 32, pl.smem);
   // phase 2
   bp.link_smem_per_warp = hb::link_smem_per_warp(bp.ucap, bp.sel_cap, pl.q_chunks);
   bp.link_warps = 8;
   while (bp.link_warps > 1 && (size_t)bp.link_warps * bp.link_smem_per_warp > (size_t)x->max_smem_optin) bp.link_warps--;
   if ((size_t)bp.link_smem_per_warp > (size_t)x->max_smem_optin) fail(HNSWB200_EINVAL, "build: dimension / num_connections too large for shared memory");
-  bp.link_grid_per_sm = std::max(1, std::min(4, (int)((size_t)(227 * 1024) / ((size_t)bp.link_warps * bp.link_smem_per_warp + 1024))));
+  bp.link_grid_per_sm = build_link_resident(pl.cpl, bp.link_warps * 32, (size_t)bp.link_warps * bp.link_smem_per_warp);
   return bp;
 }
 
@@ -91,6 +118,23 @@ void sort_keys(hnswb200_index* x, const uint64_t* in, uint64_t* out, unsigned n,
 }
 
 enum { CTR_REQ = 0, CTR_REM = 1, CTR_HEADS = 2, CTR_NEXT = 3, CTR_N = 4 };
+
+// HNSWB200_BUILD_TRACE=1: host wall time per phase (each ends at a stream synchronisation)
+struct BuildTrace {
+  bool on = std::getenv("HNSWB200_BUILD_TRACE") != nullptr;
+  double t_search = 0, t_link = 0, t_rest = 0, t_sort = 0, t_alloc = 0;
+  int64_t batches = 0, small = 0;
+  std::chrono::steady_clock::time_point t0;
+  void start() { if (on) t0 = std::chrono::steady_clock::now(); }
+  double lap() {
+    if (!on) return 0;
+    auto t1 = std::chrono::steady_clock::now();
+    double d = std::chrono::duration<double>(t1 - t0).count();
+    t0 = t1;
+    return d;
+  }
+};
+BuildTrace g_trace;
 
 // One batch: nodes [n0, n0 + B) against the graph of nodes [0, n0).
 void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, int64_t n_total) {
@@ -121,6 +165,9 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   p.heads = x->b_heads.p; p.counters = x->b_counters.p;
 
   // ---- phase 1
+  g_trace.start();
+  g_trace.batches++;
+  if (B < (int64_t)pl.grid * pl.warps) g_trace.small++;
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (B + pl.warps - 1) / pl.warps));
   switch (pl.cpl) {
     case 1: launch_build_search<1>(p, pl, grid, s); break;
@@ -133,6 +180,7 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   unsigned ctr[CTR_N];
   CUDA_CHECK(cudaMemcpyAsync(ctr, x->b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  g_trace.t_search += g_trace.lap();
   unsigned n_req = ctr[CTR_REQ];
   if (n_req > req_cap) fail(HNSWB200_ECUDA, "build: request buffer overrun");
   if (n_req == 0) return;
@@ -143,9 +191,11 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   hb::segment_heads_kernel<<<(n_req + 255) / 256, 256, 0, s>>>(x->b_req_sorted.p, n_req, hb::REQ_VBITS, x->b_heads.p,
                                                                x->b_ctr.p + CTR_HEADS);
   CUDA_CHECK(cudaGetLastError());
+  if (g_trace.on) { CUDA_CHECK(cudaStreamSynchronize(s)); g_trace.t_sort += g_trace.lap(); }
   size_t rem_cap = (size_t)n_req * (size_t)(std::max(x->slots0, x->slotsU) + 1);
   rem_cap = std::min<size_t>(rem_cap, (size_t)0xfffffff0u);
   x->b_rem.reserve_geo(rem_cap); x->b_rem_sorted.reserve_geo(rem_cap);
+  if (g_trace.on) { CUDA_CHECK(cudaStreamSynchronize(s)); g_trace.t_alloc += g_trace.lap(); }
   p.req = x->b_req_sorted.p; p.n_req = n_req;
   p.rem = x->b_rem.p; p.rem_cap = (unsigned)rem_cap;
   p.smem_per_warp = bpl.link_smem_per_warp;
@@ -161,6 +211,7 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   x->st.gpu_launches += 2;
   CUDA_CHECK(cudaMemcpyAsync(ctr, x->b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  g_trace.t_link += g_trace.lap();
   unsigned n_rem = ctr[CTR_REM];
   if (n_rem > rem_cap) fail(HNSWB200_ECUDA, "build: removal buffer overrun");
   if (n_rem == 0) return;
@@ -178,6 +229,7 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   hb::build_unlink_kernel<<<ugrid, 256, 0, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
   x->st.gpu_launches += 2;
+  g_trace.t_rest += g_trace.lap();
   (void)n_total;
 }
 
@@ -265,6 +317,18 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   int64_t max_batch = x->param_build_batch > 0 ? x->param_build_batch : 16384;
   max_batch = std::min<int64_t>(max_batch, (int64_t(1) << hb::REQ_VBITS) - 1);
   const int64_t ratio = std::max<int64_t>(1, x->param_build_ratio);
+  {
+    // scratch for the largest batch this call will run, allocated once (growing it batch by
+    // batch costs more in cudaMalloc / cudaFree than the kernels it feeds)
+    int64_t bmax = std::max<int64_t>(1, std::min<int64_t>(max_batch, std::min<int64_t>(n_new, n_tot / ratio + 1)));
+    size_t req_max = (size_t)bmax * (size_t)(bpl.sel0 + 2 * bpl.selU);
+    size_t rem_max = std::min<size_t>(req_max * (size_t)(std::max(x->slots0, x->slotsU) + 1), (size_t)0xfffffff0u);
+    x->b_req.reserve_geo(req_max); x->b_req_sorted.reserve_geo(req_max); x->b_heads.reserve_geo(req_max);
+    x->b_rem.reserve_geo(rem_max); x->b_rem_sorted.reserve_geo(rem_max);
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, x->b_rem.p, x->b_rem_sorted.p, (int)std::min<size_t>(rem_max, 0x7fffffff), 0, 64, s));
+    x->b_cub.reserve_geo(bytes + 16);
+  }
   int64_t done = n_old;
   if (done == 0) { x->entry = 0; x->max_layer = 0; done = 1; x->n = 1; }     // :774-778
   while (done < n_tot) {
@@ -286,6 +350,12 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   unsigned long long evs[2];
   CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
   if (c[3]) fail(HNSWB200_ECUDA, "build: removal buffer overflow");
+  if (g_trace.on) {
+    fprintf(stderr, "[hnsw_b200 build] n=%lld batches=%lld (under one wave: %lld) search %.3fs sort+heads %.3fs alloc %.3fs link %.3fs unlink-enqueue %.3fs dropped_incoming=%llu grid=%d x %d warps hash_slots=%d\n",
+            (long long)n_new, (long long)g_trace.batches, (long long)g_trace.small, g_trace.t_search, g_trace.t_sort, g_trace.t_alloc, g_trace.t_link, g_trace.t_rest,
+            c[2], bpl.sp.grid, bpl.sp.warps, bpl.sp.hash_slots);
+    g_trace = BuildTrace();
+  }
   x->st.build_inserts = (uint64_t)n_new;
   x->st.build_n_dist = c[0];
   x->st.build_n_exp = c[1];

@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -157,6 +159,32 @@ struct SearchPlan {
   size_t smem;
 };
 
+// resident CTAs per SM of the persistent search kernel (registers and shared memory both count);
+// cached: the query costs two driver calls
+int search_resident(int cpl, int threads, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, size_t>, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_tuple(cpl, threads, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int nb = 0;
+  switch (cpl) {
+#define HB_CASE(C)                                                                                              \
+    case C:                                                                                                     \
+      CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<C>, threads, smem));      \
+      break;
+    HB_CASE(1) HB_CASE(2) HB_CASE(3) HB_CASE(4)
+    default:
+      CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<0>, threads, smem));
+#undef HB_CASE
+  }
+  cache[key] = std::max(1, nb);
+  return std::max(1, nb);
+}
+
 // Visited set of a query: exact open-addressing hash in shared memory, or one n-bit set per warp
 // in global memory.  The hash costs shared memory (fewer resident warps: throughput is linear in
 // resident warps up to ~24 per SM); the bitset costs one global atomic round trip per expansion
@@ -202,7 +230,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   while (warps > 1 && (size_t)warps * pl.smem_per_warp > (size_t)x->max_smem_optin) warps--;
   pl.warps = warps;
   pl.smem = (size_t)warps * pl.smem_per_warp;
-  int per_sm = std::max(1, std::min(16, (int)((size_t)(227 * 1024) / (pl.smem + 1024))));
+  int per_sm = search_resident(pl.cpl, warps * 32, pl.smem);
   per_sm = std::min(per_sm, std::max(1, (per_sm_warps + warps - 1) / warps));
   int64_t need = (nq + warps - 1) / warps;
   pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * per_sm, need));

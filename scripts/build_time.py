@@ -1,0 +1,18 @@
+"""Build-time probe on the bench workload with the per-phase trace."""
+import sys, os, time
+os.environ["HNSWB200_BUILD_TRACE"] = "1"
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ocaml_hnsw_b200 as H
+from ocaml_hnsw_b200 import Ohnsw
+from bench import draw_levels
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+X = H.sift_like(n, 128, seed=1234)
+lv = draw_levels(n, 16, 7)
+for ratio, batch in [(64, 16384), (64, 16384), (32, 16384), (64, 32768), (128, 16384)]:
+    h = Ohnsw.Hgraph(128, Ohnsw.distance_l2, 16, 200)
+    h.set_param("build_ratio", ratio); h.set_param("build_batch", batch)
+    t = time.time()
+    H.capi.check(H.capi.lib().hnswb200_build(h._h, H.capi.ptr(X), n, H.capi.ptr(lv)))
+    print(f"ratio={ratio} batch={batch} wall {time.time()-t:.2f}s lib {h.stats().build_seconds:.2f}s", flush=True)
+    h.close()
