@@ -48,8 +48,9 @@ extern "C" {
 #define HNSWB200_IP 2
 
 /* search mode.  PARITY reproduces the reference's sequential best-first search id for id
- * (one expansion per iteration, exact visited set, (distance,id) tie order).  FAST may
- * expand speculatively; same result contract (k nearest found, ascending) but not id parity. */
+ * (one expansion per iteration, exact visited set, (distance,id) tie order).  FAST is reserved
+ * for a relaxed traversal (same result contract, no id parity); this version runs the PARITY
+ * kernel for both. */
 #define HNSWB200_MODE_PARITY 0
 #define HNSWB200_MODE_FAST 1
 
@@ -111,8 +112,10 @@ typedef struct hnswb200_stats {
 int hnswb200_create(hnswb200_index** out, int dim, int metric, int M, int ef_construction,
                     uint64_t seed, int device);
 int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
-/* Tunables: "hash_slots" (visited hash size per query, power of two; 0 = derive from ef),
- * "build_batch" (max inserts per GPU batch), "warps_per_cta". */
+/* Tunables (0 = automatic): "hash_slots" (visited hash slots per query), "visited_mode" (1 = shared
+ * memory hash, 2 = global bitset), "warps_per_cta", "max_warps_per_sm", "build_batch" (max inserts
+ * per GPU batch, default 16384; 1 = sequential inserts), "build_ratio" (a batch is at most
+ * n / build_ratio nodes, default 64). */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
 int hnswb200_destroy(hnswb200_index* idx);
 

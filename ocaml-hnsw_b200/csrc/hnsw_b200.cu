@@ -211,6 +211,13 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks);
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
   hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
+  {
+    // a table within ~12 % of what keeps the SM full is trimmed to fit (the few queries that
+    // outgrow it continue on a global bitset)
+    const int budget = (227 * 1024) / (4 * HB_SEARCH_MINB) - 256;
+    const int hs_fit = (budget - fixed) / 4 / 4 * 4;
+    if (x->param_hash_slots == 0 && hs > hs_fit && hs_fit * 100 >= hs * 88) hs = hs_fit;
+  }
   if (use_bitset_visited(x, ef, fixed + hs * 4, x->n)) hs = 0;
   pl.hash_slots = hs;
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
