@@ -108,6 +108,16 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def profiled_traffic(workload, ef):
+    """dram__bytes_read + write of the search kernel from the committed ncu capture, when it was
+    taken on this exact workload and ef (profiles/traffic.json); None otherwise."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["search_kernel"]
+        return t["dram_bytes_per_launch"] if (t["workload"], t["ef"]) == (workload, ef) else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -340,7 +350,8 @@ def run_ours(a):
                     "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes), "recall_at_10": round(e2e_rec, 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": profiled_traffic(workload_name(a), ef_star) if world == 1 else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
                          "dist_evals_per_query": st.search_n_dist / a.nq, "expansions_per_query": st.search_n_exp0 / a.nq,
                          "visited_spills": int(st.search_visited_overflows)},
