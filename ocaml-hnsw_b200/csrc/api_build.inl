@@ -185,6 +185,26 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   if (n_req > req_cap) fail(HNSWB200_ECUDA, "build: request buffer overrun");
   if (n_req == 0) return;
 
+  if (x->param_build_batch == 1) {
+    // sequential inserts: the reference's own link order, one warp (build.cuh, build_link_seq_kernel)
+    size_t smem = (size_t)hb::link_seq_smem(bpl.ucap, bpl.sel_cap, pl.q_chunks);
+    switch (pl.cpl) {
+#define HB_SEQ(C)                                                                                                   \
+      case C:                                                                                                       \
+        CUDA_CHECK(cudaFuncSetAttribute(hb::build_link_seq_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hb::build_link_seq_kernel<C><<<1, 32, smem, s>>>(p);                                                        \
+        break;
+      HB_SEQ(1) HB_SEQ(2) HB_SEQ(3) HB_SEQ(4)
+      default:
+        CUDA_CHECK(cudaFuncSetAttribute(hb::build_link_seq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hb::build_link_seq_kernel<0><<<1, 32, smem, s>>>(p);
+#undef HB_SEQ
+    }
+    CUDA_CHECK(cudaGetLastError());
+    x->st.gpu_launches += 1;
+    return;
+  }
+
   // ---- phase 2: sort by row, one warp per row
   sort_keys(x, x->b_req.p, x->b_req_sorted.p, n_req, 32 + hb::REQ_VBITS);
   CUDA_CHECK(cudaMemsetAsync(x->b_ctr.p + CTR_HEADS, 0, 2 * sizeof(unsigned int), s));   // heads, next

@@ -335,6 +335,144 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
   }
 }
 
+// ---- sequential link (build_batch = 1) -----------------------------------------------------------
+// One new node, one warp, the reference's own order (lib/ohnsw.ml:820-829): prepend the node to
+// every selected neighbour (set_connections_for_new_node, :198-202), then walk the neighbours in
+// list order and re-select every list that outgrew its bound, applying Graph.set_connections
+// (:182-196) at once — dropped members lose the pruned node immediately, their lists rebuilt in
+// reverse as Neighbours.remove does (:119-124).  A full row that receives the node holds one
+// entry more than its width until its turn comes: that entry is kept aside (`pend`).  With this
+// kernel a GPU build reproduces the oracle's graph edge for edge (tests/test_build_parity.py).
+__host__ __device__ inline int link_seq_smem(int ucap, int sel_cap, int q_chunks) {
+  return link_smem_per_warp(ucap, sel_cap, q_chunks) + 3 * sel_cap * 4;
+}
+
+// list_r := reverse(filter(!= a, logical list of r)), where the logical list is [v] + row when pending
+__device__ __forceinline__ void seq_remove(int32_t* row, int slots, bool pending, uint32_t v, uint32_t a, uint32_t* tmp, int lane) {
+  int n = 0;
+  if (pending) { if (lane == 0 && v != a) tmp[0] = v; n = v != a ? 1 : 0; }
+  for (int r0 = 0; r0 < slots; r0 += 32) {
+    int nb = r0 + lane < slots ? row[r0 + lane] : -1;
+    unsigned valid = __ballot_sync(FULL, nb >= 0);
+    bool keep = nb >= 0 && (uint32_t)nb != a;
+    unsigned km = __ballot_sync(FULL, keep);
+    if (keep) tmp[n + __popc(km & ((1u << lane) - 1u))] = (uint32_t)nb;
+    n += __popc(km);
+    if (valid != FULL) break;
+  }
+  __syncwarp();
+  for (int j = lane; j < slots; j += 32) row[j] = j < n ? (int32_t)tmp[n - 1 - j] : -1;
+  __syncwarp();
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(32) build_link_seq_kernel(const BuildParams bp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GraphView& g = bp.sp.g;
+  const int lane = threadIdx.x & 31;
+  uint64_t* ukey = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* sorted = ukey + bp.ucap;
+  float4* qs = reinterpret_cast<float4*>(sorted + bp.ucap);
+  float4* qs2 = qs + bp.sp.q_smem_chunks;
+  uint32_t* uid = reinterpret_cast<uint32_t*>(qs2 + bp.sp.q_smem_chunks);
+  float* ud = reinterpret_cast<float*>(uid + bp.ucap);
+  uint32_t* sel = reinterpret_cast<uint32_t*>(ud + bp.ucap);
+  float* newd = reinterpret_cast<float*>(sel + bp.sel_cap);
+  uint32_t* nbs = reinterpret_cast<uint32_t*>(newd + 32);       // the new node's list on this layer
+  uint32_t* pend = nbs + bp.sel_cap;                            // 1: the node is logically at the head of that neighbour's full row
+  uint32_t* rem = pend + bp.sel_cap;                            // dropped members of one pruned list
+  float4 qa[CPL > 0 ? CPL : 1], qe[CPL > 0 ? CPL : 1];
+  const uint32_t v = (uint32_t)bp.n0;
+  uint32_t n_dist = 0;
+  for (int layer = min((int)bp.level[v], g.max_layer); layer >= 0; layer--) {
+    const int slots = layer == 0 ? g.slots0 : g.slotsU;
+    const int nc = layer == 0 ? bp.cap0 : bp.capU;
+    const int32_t* row_v = row_ptr(bp, row_id(g, v, layer));
+    int nsel = 0;
+    for (int r0 = 0; r0 < slots; r0 += 32) {
+      int nb = r0 + lane < slots ? row_v[r0 + lane] : -1;
+      unsigned valid = __ballot_sync(FULL, nb >= 0);
+      if (nb >= 0) nbs[r0 + lane] = (uint32_t)nb;
+      nsel += __popc(valid);
+      if (valid != FULL) break;
+    }
+    __syncwarp();
+    // set_connections_for_new_node: Neighbours.add node on every selected neighbour
+    for (int j = 0; j < nsel; j++) {
+      int32_t* row = row_ptr(bp, row_id(g, nbs[j], layer));
+      int deg = 0;
+      for (int r0 = 0; r0 < slots; r0 += 32) {
+        int nb = r0 + lane < slots ? row[r0 + lane] : -1;
+        unsigned valid = __ballot_sync(FULL, nb >= 0);
+        if (nb >= 0) uid[r0 + lane] = (uint32_t)nb;
+        deg += __popc(valid);
+        if (valid != FULL) break;
+      }
+      __syncwarp();
+      if (deg < slots && deg < nc + 1 && deg + 1 <= slots) {
+        for (int i = lane; i <= deg; i += 32) row[i] = i == 0 ? (int32_t)v : (int32_t)uid[i - 1];
+        if (lane == 0) pend[j] = 0u;
+      } else if (lane == 0) pend[j] = 1u;
+      __syncwarp();
+    }
+    // re-select the lists that outgrew nc, in list order
+    for (int j = 0; j < nsel; j++) {
+      const uint32_t a = nbs[j];
+      int32_t* row = row_ptr(bp, row_id(g, a, layer));
+      const bool pj = pend[j] != 0u;
+      int u = pj ? 1 : 0;
+      if (pj && lane == 0) uid[0] = v;
+      for (int r0 = 0; r0 < slots; r0 += 32) {
+        int nb = r0 + lane < slots ? row[r0 + lane] : -1;
+        unsigned valid = __ballot_sync(FULL, nb >= 0);
+        if (nb >= 0) uid[u + __popc(valid & ((1u << lane) - 1u))] = (uint32_t)nb;
+        u += __popc(valid);
+        if (valid != FULL) break;
+      }
+      __syncwarp();
+      if (u <= nc) continue;                                              // :823
+      load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)a * g.ld4, qa, qs, lane);
+      batch_dist<CPL>(g, CPL > 0 ? qa : nullptr, qs, uid, ud, u, lane);   // min_queue_of_neighbours (:791-798)
+      n_dist += u;
+      for (int i = lane; i < u; i += 32) ukey[i] = make_key(ud[i], uid[i]);
+      __syncwarp();
+      warp_rank_sort(ukey, sorted, u, lane);
+      int ns = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist);   // :824-826
+      for (int i = lane; i < slots; i += 32) row[i] = i < ns ? (int32_t)sel[ns - 1 - i] : -1;   // Graph.set_connections step 1
+      if (lane == 0) pend[j] = 0u;
+      // step 2: removed = old \ new, walked in ascending id (Set.iter)
+      int nr = 0;
+      for (int i0 = 0; i0 < u; i0 += 32) {
+        int i = i0 + lane;
+        bool out = i < u && !(sorted[i] & 1ull);
+        unsigned bm = __ballot_sync(FULL, out);
+        if (out) rem[nr + __popc(bm & ((1u << lane) - 1u))] = key_id(sorted[i]);
+        nr += __popc(bm);
+      }
+      __syncwarp();
+      for (int done = 0; done < nr; done++) {
+        // next smallest id not yet handled (nr is small: selection sort by warp minimum)
+        uint32_t best = 0xffffffffu;
+        for (int i = lane; i < nr; i += 32) best = min(best, rem[i]);
+        best = __reduce_min_sync(FULL, best);
+        __syncwarp();
+        for (int i = lane; i < nr; i += 32) if (rem[i] == best) rem[i] = 0xffffffffu;
+        __syncwarp();
+        bool pr = false;
+        int jr = -1;
+        for (int i = lane; i < nsel; i += 32) if (nbs[i] == best) jr = i;
+        jr = __reduce_max_sync(FULL, jr);
+        if (jr >= 0) pr = pend[jr] != 0u;
+        int32_t* rrow = row_ptr(bp, row_id(g, best, layer));
+        seq_remove(rrow, slots, pr, v, a, uid, lane);
+        if (jr >= 0 && lane == 0) pend[jr] = 0u;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) atomicAdd(bp.counters + 0, (unsigned long long)n_dist);
+}
+
 // ---- phase 3 --------------------------------------------------------------------------------------
 // One warp per row named in the sorted removal requests: drop every owner listed for it.
 __global__ void __launch_bounds__(256) build_unlink_kernel(const BuildParams bp) {

@@ -95,6 +95,42 @@ def test_search_on_gpu_built_graph_is_exact(built20k):
         assert np.array_equal(h.last_search_counters(500).astype(np.uint64), cnt_o)
 
 
+def _same_graph(g, go):
+    assert (g.n, g.max_layer, g.entry) == (go.n, go.max_layer, go.entry)
+    assert np.array_equal(g.levels, go.levels)
+    for l in range(g.max_layer + 1):
+        assert np.array_equal(g.offsets[l], go.offsets[l]), f"layer {l}: degrees differ"
+        bad = np.nonzero(g.nbrs[l] != go.nbrs[l])[0]
+        assert bad.size == 0, f"layer {l}: {bad.size} adjacency slots differ (first at {bad[:3]})"
+
+
+@pytest.mark.parametrize("kind,n,dim,M,efC", [("uniform", 1500, 32, 6, 30), ("sift", 1200, 128, 16, 60),
+                                               ("ints", 1000, 8, 5, 25), ("uniform", 600, 100, 4, 40)])
+def test_sequential_gpu_build_is_the_oracle_graph(kind, n, dim, M, efC):
+    """build_batch = 1: inserts one at a time through the sequential link kernel — the GPU-built
+    graph must be the oracle's (= the reference's, lib/ohnsw.ml:766-837) edge for edge, list order
+    included, also on tie-heavy integer data."""
+    if kind == "uniform":
+        X = uniform(n, dim, 41)
+    elif kind == "sift":
+        X = H.sift_like(n, dim, seed=42)
+    else:
+        X = np.random.default_rng(43).integers(0, 5, (n, dim)).astype(np.float32)
+        X = np.unique(X, axis=0)                       # duplicate vectors make the heuristic degenerate; keep ties only
+        X = X[np.random.default_rng(44).permutation(len(X))]
+        n = len(X)
+    lv = draw_levels(n, M)
+    lv[0] = 0
+    o = O.VecOracle(dim).build(X, M, efC, lv)
+    h = Ohnsw.Hgraph(dim, Ohnsw.distance_l2, M, efC)
+    h.set_param("build_batch", 1)
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), n, capi.ptr(lv)))
+    _same_graph(h.export_graph(), o.export())
+    # distance evaluations: the search part counts exactly like the oracle; selection evaluates
+    # kept-vs-candidate distances eight at a time where the reference stops at the first failure
+    assert h.stats().build_n_dist >= o.counters()[0] * 0.9
+
+
 def test_build_is_deterministic():
     X = uniform(6000, 64, 5)
     lv = draw_levels(len(X), 8)
