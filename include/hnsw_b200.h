@@ -175,6 +175,11 @@ int hnswb200_export_levels(hnswb200_index* idx, int32_t* levels);
 int hnswb200_bruteforce_knn(const float* data, int64_t n, const float* queries, int64_t nq, int dim,
                             int k, int metric, int device, int32_t* ids, float* dists);
 
+/* How the last hnswb200_bruteforce_knn call on this thread ran: -1 = fp32 CUDA-core kernel only;
+ * >= 0 = tensor-core ranking + exact fp32 re-rank, the value being the number of queries whose
+ * result it could not prove exact (when not zero the whole batch was recomputed in fp32). */
+int64_t hnswb200_bruteforce_last_unproven(void);
+
 /* Replaces Recall.compute (benchmark/dataset.ml:105-127) on `[nq][k]` arrays. */
 int hnswb200_recall(const float* expected, const float* got, int64_t nq, int k, double epsilon,
                     double* out);

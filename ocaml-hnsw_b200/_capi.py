@@ -57,6 +57,7 @@ SIGNATURES = {
     "hnswb200_export_layer": (_i32, [_vp, _i32, _i32, _vp, _vp, C.POINTER(_i64)]),
     "hnswb200_export_levels": (_i32, [_vp, _vp]),
     "hnswb200_bruteforce_knn": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hnswb200_bruteforce_last_unproven": (_i64, []),
     "hnswb200_recall": (_i32, [_vp, _vp, _i64, _i32, _f64, C.POINTER(_f64)]),
     "hnswb200_merge_topk_device": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     "hnswb200_get_info": (_i32, [_vp, C.POINTER(Info)]),

@@ -1,5 +1,6 @@
 // C ABI: brute-force ground truth and shard merge (included by hnsw_b200.cu).
 namespace {
+thread_local int64_t g_last_bruteforce_unproven = -1;   // -1: tensor-core path not taken
 void launch_bruteforce(const float* d_data, int64_t n, const float* d_q, int64_t nq, int ld, int k, int metric,
                        int num_sms, int32_t* d_ids, float* d_dists, cudaStream_t s, uint64_t* launches) {
   int k_cap = round_up(k, 32);
@@ -22,6 +23,64 @@ void launch_bruteforce(const float* d_data, int64_t n, const float* d_q, int64_t
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaStreamSynchronize(s));
   if (launches) *launches += 2;
+}
+// Tensor-core path (bruteforce_tc.cuh): returns the number of queries whose result could not be
+// proven exact (the caller recomputes with the fp32 kernel when that is not zero).
+int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, int64_t nq, int ld, int dim, int k,
+                             int num_sms, int32_t* d_ids, float* d_dists, cudaStream_t s, uint64_t* launches) {
+  const int kp = round_up(dim, hb::TC_KC);
+  DevBuf<__nv_bfloat16> x_hi, x_lo, q_hi, q_lo;
+  DevBuf<float> x_norm, scal, bound;
+  DevBuf<int> flags;
+  DevBuf<uint64_t> partial;
+  x_hi.reserve((size_t)n * kp); x_lo.reserve((size_t)n * kp); q_hi.reserve((size_t)nq * kp); q_lo.reserve((size_t)nq * kp);
+  x_norm.reserve((size_t)n); scal.reserve(4); flags.reserve((size_t)nq + 4);
+  CUDA_CHECK(cudaMemsetAsync(scal.p, 0, 4 * sizeof(float), s));     // [0] max ||x||^2, [1] any lo (int), [2] max ||q||^2 (unused)
+  int wpb = 8;
+  hb::bf16_split_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_data, ld, dim, n, kp, x_hi.p, x_lo.p, x_norm.p,
+                                                                            reinterpret_cast<int*>(scal.p + 1), scal.p);
+  hb::bf16_split_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_q, ld, dim, nq, kp, q_hi.p, q_lo.p, nullptr,
+                                                                             reinterpret_cast<int*>(scal.p + 1), scal.p + 2);
+  CUDA_CHECK(cudaGetLastError());
+  float h_scal[4];
+  CUDA_CHECK(cudaMemcpyAsync(h_scal, scal.p, sizeof(h_scal), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  int any_lo; memcpy(&any_lo, &h_scal[1], 4);
+
+  const int qblocks = (int)((nq + hb::TC_M - 1) / hb::TC_M);
+  int splits = std::max(1, std::min(16, (8 * num_sms + qblocks - 1) / qblocks));       // >= ~8 waves of CTAs
+  int64_t split_len = ((n + splits - 1) / splits + hb::TC_N - 1) / hb::TC_N * hb::TC_N;
+  splits = (int)((n + split_len - 1) / split_len);
+  partial.reserve((size_t)splits * nq * hb::TC_KP);
+  bound.reserve((size_t)splits * nq);
+  hb::TcParams p{};
+  p.x_hi = x_hi.p; p.x_lo = x_lo.p; p.q_hi = q_hi.p; p.q_lo = q_lo.p; p.x_norm = x_norm.p;
+  p.n = n; p.nq = nq; p.kp = kp; p.segs = any_lo ? 3 : 1; p.split_len = split_len; p.partial = partial.p; p.bound = bound.p;
+  size_t smem = hb::tc_smem_bytes();
+  CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hb::bruteforce_tc_kernel<<<dim3(qblocks, splits), hb::TC_THREADS, smem, s>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+
+  hb::TcFinishParams f{};
+  f.g.vec = d_data; f.g.ld4 = ld / 4; f.g.chunks = ld / 4; f.g.metric = 0; f.g.n = (int)n;
+  f.queries = d_q; f.partial = partial.p; f.bound = bound.p; f.S = splits; f.nq = nq; f.k = k; f.k_cap = round_up(k, 32);
+  f.q_chunks = round_up(ld / 4, 2);
+  f.smem_per_warp = hb::tc_finish_smem_per_warp(f.k_cap, f.q_chunks);
+  f.eps = any_lo ? 1.0f / 4096.0f : 1.0f / 65536.0f;
+  f.max_norm = scal.p; f.ids = d_ids; f.dists = d_dists; f.flags = flags.p;
+  int fw = 8;
+  while (fw > 1 && (size_t)fw * f.smem_per_warp > 200 * 1024) fw--;
+  size_t fsmem = (size_t)fw * f.smem_per_warp;
+  CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  hb::bruteforce_tc_finish_kernel<<<(unsigned)((nq + fw - 1) / fw), fw * 32, fsmem, s>>>(f);
+  CUDA_CHECK(cudaGetLastError());
+  std::vector<int> h_flags((size_t)nq);
+  CUDA_CHECK(cudaMemcpyAsync(h_flags.data(), flags.p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (launches) *launches += 4;
+  int64_t bad = 0;
+  for (int v : h_flags) bad += v != 0;
+  return bad;
 }
 }  // namespace
 
@@ -47,11 +106,20 @@ int hnswb200_bruteforce_knn(const float* data, int64_t n, const float* queries, 
     d_data.reserve((size_t)n * ld); d_q.reserve((size_t)nq * ld); d_d.reserve((size_t)nq * k); d_i.reserve((size_t)nq * k);
     upload_rows(d_data.p, ld, data, dim, n, 0);
     upload_rows(d_q.p, ld, queries, dim, nq, 0);
-    launch_bruteforce(d_data.p, n, d_q.p, nq, ld, k, metric, prop.multiProcessorCount, d_i.p, d_d.p, 0, nullptr);
+    // L2 and k <= 32: tensor cores rank the candidates, fp32 re-ranks and proves exactness; anything it
+    // cannot prove (and every other case) goes through the fp32 CUDA-core kernel.
+    const char* force = std::getenv("HNSWB200_BRUTEFORCE");
+    bool tc = metric == HNSWB200_L2 && k <= hb::TC_KP && n >= hb::TC_N && !(force && std::string(force) == "fp32");
+    int64_t unproven = tc ? launch_bruteforce_tc(d_data.p, n, d_q.p, nq, ld, dim, k, prop.multiProcessorCount, d_i.p, d_d.p, 0, nullptr) : -1;
+    g_last_bruteforce_unproven = unproven;
+    if (unproven != 0)
+      launch_bruteforce(d_data.p, n, d_q.p, nq, ld, k, metric, prop.multiProcessorCount, d_i.p, d_d.p, 0, nullptr);
     if (ids) CUDA_CHECK(cudaMemcpy(ids, d_i.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(dists, d_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost));
   });
 }
+
+int64_t hnswb200_bruteforce_last_unproven(void) { return g_last_bruteforce_unproven; }
 
 int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n_shards, int64_t nq, int k,
                                const int64_t* shard_offsets, int32_t* d_out_ids, float* d_out_dists, void* stream) {

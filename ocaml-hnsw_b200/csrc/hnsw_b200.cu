@@ -19,6 +19,7 @@
 #include "search.cuh"
 #include "build.cuh"
 #include "bruteforce.cuh"
+#include "bruteforce_tc.cuh"
 #include "merge.cuh"
 
 namespace {

@@ -29,6 +29,29 @@ def test_bruteforce_matches_oracle(n, nq, dim, k):
     assert H.Recall.compute(d_o, d_g, epsilon=1e-4) > 0.999
 
 
+@pytest.mark.parametrize("kind,n,nq,dim,k", [("uniform", 20000, 300, 128, 10), ("sift", 30000, 500, 128, 10), ("uniform", 5000, 130, 100, 32),
+                                              ("normal", 8000, 64, 960, 10), ("uniform", 1000, 257, 20, 1)])
+def test_bruteforce_tensor_core_path_is_exact(kind, n, nq, dim, k):
+    """L2, k <= 32, n >= 256 runs on tcgen05 (bf16 hi/lo split GEMM ranks, fp32 re-ranks and proves):
+    the result must be the oracle's, ids and distances bit for bit (re-rank uses the oracle's order)."""
+    if kind == "sift":
+        X, Q = H.sift_like(n, dim, seed=5), H.sift_like(nq, dim, seed=6)
+    elif kind == "normal":
+        X = np.random.default_rng(7).standard_normal((n, dim)).astype(np.float32) * 3
+        Q = np.random.default_rng(8).standard_normal((nq, dim)).astype(np.float32) * 3
+    else:
+        X, Q = uniform(n, dim, 3), uniform(nq, dim, 4)
+    ids_g, d_g = H.brute_force_knn_l2(X, Q, k, return_ids=True)
+    unproven = capi.lib().hnswb200_bruteforce_last_unproven()
+    assert unproven >= 0, "tensor-core path was not taken"
+    ids_o, d_o = O.bruteforce(X, Q, k)
+    if unproven == 0:
+        assert np.array_equal(ids_g, ids_o) and np.array_equal(d_g.view(np.uint32), d_o.view(np.uint32))
+    else:
+        _same_up_to_ties(ids_g, d_g, ids_o, d_o)
+    assert unproven <= nq // 50, f"{unproven} of {nq} queries fell back to fp32"
+
+
 def test_bruteforce_pads_when_k_exceeds_n():
     X, Q = uniform(20, 16, 3), uniform(3, 16, 4)
     ids_g, d_g = H.brute_force_knn_l2(X, Q, 32, return_ids=True)
