@@ -1,6 +1,22 @@
 // C ABI: brute-force ground truth and shard merge (included by hnsw_b200.cu).
 namespace {
 thread_local int64_t g_last_bruteforce_unproven = -1;   // -1: tensor-core path not taken
+
+// HNSWB200_TRACE=1: device time of the brute-force kernels (CUDA events) on stderr
+struct EvTimer {
+  bool on = std::getenv("HNSWB200_TRACE") != nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  explicit EvTimer(cudaStream_t st) : s(st) { if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); } }
+  void lap(const char* what) {
+    if (!on) return;
+    cudaEventRecord(b, s); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    fprintf(stderr, "[hnsw_b200 bruteforce] %s %.3f ms\n", what, ms);
+    cudaEventRecord(a, s);
+  }
+  ~EvTimer() { if (on) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
 void launch_bruteforce(const float* d_data, int64_t n, const float* d_q, int64_t nq, int ld, int k, int metric,
                        int num_sms, int32_t* d_ids, float* d_dists, cudaStream_t s, uint64_t* launches) {
   int k_cap = round_up(k, 32);
@@ -16,8 +32,10 @@ void launch_bruteforce(const float* d_data, int64_t n, const float* d_q, int64_t
   p.data = d_data; p.queries = d_q; p.n = n; p.nq = nq; p.ld = ld; p.k = k; p.k_cap = k_cap; p.metric = metric;
   p.split_len = split_len; p.partial = partial.p;
   CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EvTimer tm(s);
   hb::bruteforce_kernel<<<dim3(qblocks, splits), hb::BF_THREADS, smem, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
+  tm.lap("fp32 bruteforce_kernel");
   int wpb = 8;
   hb::bruteforce_finish_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, s>>>(partial.p, splits, nq, k, metric, d_ids, d_dists);
   CUDA_CHECK(cudaGetLastError());
@@ -37,18 +55,20 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   x_norm.reserve((size_t)n); scal.reserve(4); flags.reserve((size_t)nq + 4);
   CUDA_CHECK(cudaMemsetAsync(scal.p, 0, 4 * sizeof(float), s));     // [0] max ||x||^2, [1] any lo (int), [2] max ||q||^2 (unused)
   int wpb = 8;
+  EvTimer tm(s);
   hb::bf16_split_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_data, ld, dim, n, kp, x_hi.p, x_lo.p, x_norm.p,
                                                                             reinterpret_cast<int*>(scal.p + 1), scal.p);
   hb::bf16_split_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_q, ld, dim, nq, kp, q_hi.p, q_lo.p, nullptr,
                                                                              reinterpret_cast<int*>(scal.p + 1), scal.p + 2);
   CUDA_CHECK(cudaGetLastError());
+  tm.lap("bf16_split_kernel x2");
   float h_scal[4];
   CUDA_CHECK(cudaMemcpyAsync(h_scal, scal.p, sizeof(h_scal), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   int any_lo; memcpy(&any_lo, &h_scal[1], 4);
 
   const int qblocks = (int)((nq + hb::TC_M - 1) / hb::TC_M);
-  int splits = std::max(1, std::min(16, (8 * num_sms + qblocks - 1) / qblocks));       // >= ~8 waves of CTAs
+  int splits = std::max(1, std::min(32, (8 * num_sms + qblocks - 1) / qblocks));       // >= ~8 waves of CTAs
   int64_t split_len = ((n + splits - 1) / splits + hb::TC_N - 1) / hb::TC_N * hb::TC_N;
   splits = (int)((n + split_len - 1) / split_len);
   partial.reserve((size_t)splits * nq * hb::TC_KP);
@@ -58,8 +78,10 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   p.n = n; p.nq = nq; p.kp = kp; p.segs = any_lo ? 3 : 1; p.split_len = split_len; p.partial = partial.p; p.bound = bound.p;
   size_t smem = hb::tc_smem_bytes();
   CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tm.lap("(sync, alloc)");
   hb::bruteforce_tc_kernel<<<dim3(qblocks, splits), hb::TC_THREADS, smem, s>>>(p);
   CUDA_CHECK(cudaGetLastError());
+  tm.lap(p.segs == 3 ? "bruteforce_tc_kernel (3 segments)" : "bruteforce_tc_kernel (1 segment)");
 
   hb::TcFinishParams f{};
   f.g.vec = d_data; f.g.ld4 = ld / 4; f.g.chunks = ld / 4; f.g.metric = 0; f.g.n = (int)n;
@@ -74,6 +96,7 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   hb::bruteforce_tc_finish_kernel<<<(unsigned)((nq + fw - 1) / fw), fw * 32, fsmem, s>>>(f);
   CUDA_CHECK(cudaGetLastError());
+  tm.lap("bruteforce_tc_finish_kernel");
   std::vector<int> h_flags((size_t)nq);
   CUDA_CHECK(cudaMemcpyAsync(h_flags.data(), flags.p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -106,7 +129,7 @@ int hnswb200_bruteforce_knn(const float* data, int64_t n, const float* queries, 
     d_data.reserve((size_t)n * ld); d_q.reserve((size_t)nq * ld); d_d.reserve((size_t)nq * k); d_i.reserve((size_t)nq * k);
     upload_rows(d_data.p, ld, data, dim, n, 0);
     upload_rows(d_q.p, ld, queries, dim, nq, 0);
-    // L2 and k <= 32: tensor cores rank the candidates, fp32 re-ranks and proves exactness; anything it
+    // L2 and k <= 16: tensor cores rank the candidates, fp32 re-ranks and proves exactness; anything it
     // cannot prove (and every other case) goes through the fp32 CUDA-core kernel.
     const char* force = std::getenv("HNSWB200_BRUTEFORCE");
     bool tc = metric == HNSWB200_L2 && k <= hb::TC_KP && n >= hb::TC_N && !(force && std::string(force) == "fp32");

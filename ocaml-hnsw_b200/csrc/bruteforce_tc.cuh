@@ -27,12 +27,13 @@ constexpr int TC_M = 128;        // queries per CTA            (UMMA M)
 constexpr int TC_N = 256;        // data rows per accumulator  (UMMA N)
 constexpr int TC_KC = 64;        // bf16 elements per k-chunk: 128 bytes per row, four K=16 MMAs
 constexpr int TC_STAGES = 3;
-constexpr int TC_KP = 32;        // candidates kept per query per split
+constexpr int TC_KP = 16;        // candidates kept per query per split (shorter sorted lists: the epilogue is the bottleneck)
 constexpr int TC_THREADS = 128;
 constexpr int TC_A_BYTES = TC_M * TC_KC * 2;
 constexpr int TC_B_BYTES = TC_N * TC_KC * 2;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_LIST_LD = TC_KP + 1;      // padded: one list per thread, stride 33 keys
+constexpr int TC_STAGE_CAP = 8;            // staged candidates per thread between list updates
+constexpr int TC_LIST_LD = TC_KP + TC_STAGE_CAP + 1;   // one sorted list + stage per thread, odd stride (bank spread)
 constexpr uint32_t TC_TMEM_COLS = 256;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = BF16 (bits 7, 10),
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
   const uint32_t tmem = *tmem_slot;
 
   uint64_t* my_list = lists + (size_t)tid * TC_LIST_LD;
+  uint64_t* my_stage = my_list + TC_KP;
   int cnt = 0;
   float thr = __int_as_float(0x7f800000);
 
@@ -217,28 +219,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
     if (c == nchunks - 1) {
       // ---- epilogue of this tile: one accumulator row (query) per thread
       const int64_t xb = x_begin + tile * TC_N;
-      for (int i = tid; i < TC_N; i += TC_THREADS) xn[i] = xb + i < x_end ? p.x_norm[xb + i] : 0.f;
+      for (int i = tid; i < TC_N; i += TC_THREADS) xn[i] = xb + i < x_end ? p.x_norm[xb + i] : __int_as_float(0x7f800000);
       mbar_wait(smem_u32(bars + TC_STAGES), (uint32_t)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __syncthreads();
+      // Candidates that beat the thread's threshold are only STAGED while the columns stream by;
+      // the sorted list is updated once per tile (and when the stage fills), so a warp pays for
+      // the longest stage of its 32 threads per tile, not for every thread's every hit.
+      int ns = 0;
+      auto flush = [&]() {
+        for (int e = 0; e < ns; e++) {
+          const uint64_t key = my_stage[e];
+          if (cnt == TC_KP && key >= my_list[TC_KP - 1]) continue;
+          int pos = cnt < TC_KP ? cnt : TC_KP - 1;
+          while (pos > 0 && my_list[pos - 1] > key) { my_list[pos] = my_list[pos - 1]; pos--; }
+          my_list[pos] = key;
+          if (cnt < TC_KP) cnt++;
+        }
+        ns = 0;
+        if (cnt == TC_KP) thr = key_dist(my_list[TC_KP - 1]);
+      };
 #pragma unroll 1
       for (int cb = 0; cb < TC_N / 32; cb++) {
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), r);
+        const float4* xn4 = reinterpret_cast<const float4*>(xn + cb * 32);
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int col = cb * 32 + j;
-          const float d = fmaf(-2.f, __uint_as_float(r[j]), xn[col]);
-          if (d < thr && xb + col < x_end) {
-            const uint64_t key = make_key(d, (uint32_t)(xb + col));
-            int pos = cnt < TC_KP ? cnt : TC_KP - 1;
-            while (pos > 0 && my_list[pos - 1] > key) { my_list[pos] = my_list[pos - 1]; pos--; }
-            my_list[pos] = key;
-            if (cnt < TC_KP) cnt++;
-            if (cnt == TC_KP) thr = key_dist(my_list[TC_KP - 1]);
+        for (int j4 = 0; j4 < 8; j4++) {
+          const float4 nv = xn4[j4];
+          const float nn[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int j = j4 * 4 + u, col = cb * 32 + j;
+            const float d = fmaf(-2.f, __uint_as_float(r[j]), nn[u]);     // columns past the end carry +inf norms
+            if (d < thr) {
+              my_stage[ns++] = make_key(d, (uint32_t)(xb + col));
+              if (ns == TC_STAGE_CAP) flush();
+            }
           }
         }
       }
+      flush();
       // the next tile's first MMA overwrites the accumulator: order it after every thread's reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
@@ -299,7 +320,7 @@ __global__ void __launch_bounds__(256) bruteforce_tc_finish_kernel(const TcFinis
   for (int s = 0; s < p.S; s++) {
     const uint64_t* list = p.partial + ((size_t)s * p.nq + q) * TC_KP;
     min_bound = fminf(min_bound, p.bound[(size_t)s * p.nq + q]);
-    const uint64_t key = list[lane];                       // TC_KP == 32: one candidate per lane
+    const uint64_t key = lane < TC_KP ? list[lane] : KEY_INF;
     const unsigned m = __ballot_sync(FULL, key != KEY_INF);
     const int cnt = __popc(m);
     if (!cnt) continue;
