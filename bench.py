@@ -7,8 +7,8 @@ plus index build seconds.
     python bench.py --impl reference [...]                          # the reference's CPU path (oracle port)
 
 One "step" = one pass of the hot path over one batch: a batched k-NN search of all 10k queries
-(Ohnsw.knn_batch_bigarray, lib/ohnsw.ml:877-897) at the smallest ef of the sweep whose recall@10
-is >= 0.95.  The index is built once, on the GPU, before the timed region (build seconds are
+(Ohnsw.knn_batch_bigarray, lib/ohnsw.ml:877-897) at the smallest ef whose recall@10 is >= 0.95
+(coarse sweep, then bisection).  The index is built once, on the GPU, before the timed region (build seconds are
 reported beside the QPS).  `value` times the search with queries resident in HBM; `e2e` times the
 public host-buffer call (pinned H2D of the queries + search + D2H of ids and distances).
 
@@ -149,15 +149,28 @@ def run_reference(a):
     build_s = time.time() - t0
     gt_n = min(a.nq, 2000)
     gt, _ = O.bruteforce(X, Q[:gt_n], a.k)
-    ef_star, rec = EF_SWEEP[-1], 0.0
+    def recall_at(ef):
+        ids = o.search_mt(Q[:gt_n], a.k, ef)[0]
+        return float(np.mean([len(set(g.tolist()) & set(i[i >= 0].tolist())) / a.k for g, i in zip(gt, ids)]))
+
+    ef_star, rec, prev = EF_SWEEP[-1], 0.0, None
     for ef in EF_SWEEP:
         if ef < a.k:
             continue
-        ids = o.search_mt(Q[:gt_n], a.k, ef)[0]
-        rec = float(np.mean([len(set(g.tolist()) & set(i[i >= 0].tolist())) / a.k for g, i in zip(gt, ids)]))
+        rec = recall_at(ef)
         if rec >= a.target_recall:
             ef_star = ef
             break
+        prev = ef
+    if prev is not None and rec >= a.target_recall:          # same bisection refinement as the GPU arm
+        lo_ef, hi_ef = prev, ef_star
+        while hi_ef - lo_ef > 1:
+            mid = (lo_ef + hi_ef) // 2
+            r = recall_at(mid)
+            if r >= a.target_recall:
+                hi_ef, ef_star, rec = mid, mid, r
+            else:
+                lo_ef = mid
     for _ in range(a.warmup):
         o.search_mt(Q, a.k, ef_star)
     secs = 0.0
@@ -234,7 +247,7 @@ def run_ours(a):
         gd = gather_rows(torch.from_numpy(gt_d_l).to(dev), world)
         go_i = torch.empty((a.nq, a.k), dtype=torch.int32, device=dev)
         go_d = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
-        capi.check(capi.lib().hnswb200_merge_topk_device(gi.data_ptr(), gd.data_ptr(), world, a.nq, a.k,
+        capi.check(capi.lib().hnswb200_merge_topk_device(gi.data_ptr(), gd.data_ptr(), world, a.nq, a.k, 0,
                                                          capi.ptr(sh.offsets), go_i.data_ptr(), go_d.data_ptr(), None))
         gt_ids = go_i.cpu().numpy()
     else:
@@ -262,6 +275,19 @@ def run_ours(a):
             break
     if ef_star is None:
         ef_star, rec_star = sweep[-1]
+    elif len(sweep) >= 2:
+        # refine between the last failing and the first passing ef of the coarse sweep (bisection)
+        lo_ef, hi_ef = sweep[-2][0], ef_star
+        while hi_ef - lo_ef > 1:
+            mid = (lo_ef + hi_ef) // 2
+            ids, _ = search_dev(mid)
+            stream.synchronize()
+            rec = H.Recall.ids(gt_ids, ids.cpu().numpy())
+            sweep.append((mid, round(rec, 4)))
+            if rec >= a.target_recall:
+                hi_ef, ef_star, rec_star = mid, mid, rec
+            else:
+                lo_ef = mid
     # ---- timed region: K search steps, queries resident in HBM
     for _ in range(a.warmup):
         search_dev(ef_star)

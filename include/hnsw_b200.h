@@ -187,12 +187,14 @@ int hnswb200_recall(const float* expected, const float* got, int64_t nq, int k, 
 /* ---- multi-GPU: per-shard top-k merge ------------------------------------------ */
 
 /* After an all-gather of per-shard results: d_ids/d_dists are `[n_shards][nq][k]` in device
- * memory, ids local to each shard; `shard_offsets` (host, int64[n_shards], NULL = all zero) is
- * the first global row of each shard.  Merged into the k best per query `[nq][k]` with global
- * ids, ascending by (distance, id), -1/NaN padded.  `stream` NULL = default stream, synchronous. */
+ * memory, ids local to each shard, consecutive shards `shard_stride` elements apart (0 = nq * k;
+ * 2 * nq * k when every rank contributes one packed `[ids | dists]` block to a single
+ * all-gather); `shard_offsets` (host, int64[n_shards], NULL = all zero) is the first global row
+ * of each shard.  Merged into the k best per query `[nq][k]` with global ids, ascending by
+ * (distance, id), -1/NaN padded.  `stream` NULL = default stream, synchronous. */
 int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n_shards, int64_t nq,
-                               int k, const int64_t* shard_offsets, int32_t* d_out_ids,
-                               float* d_out_dists, void* stream);
+                               int k, int64_t shard_stride, const int64_t* shard_offsets,
+                               int32_t* d_out_ids, float* d_out_dists, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 

@@ -59,7 +59,7 @@ SIGNATURES = {
     "hnswb200_bruteforce_knn": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hnswb200_bruteforce_last_unproven": (_i64, []),
     "hnswb200_recall": (_i32, [_vp, _vp, _i64, _i32, _f64, C.POINTER(_f64)]),
-    "hnswb200_merge_topk_device": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "hnswb200_merge_topk_device": (_i32, [_vp, _vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
     "hnswb200_get_info": (_i32, [_vp, C.POINTER(Info)]),
     "hnswb200_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "hnswb200_host_register": (_i32, [_vp, _i64]),

@@ -145,11 +145,14 @@ int hnswb200_bruteforce_knn(const float* data, int64_t n, const float* queries, 
 int64_t hnswb200_bruteforce_last_unproven(void) { return g_last_bruteforce_unproven; }
 
 int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n_shards, int64_t nq, int k,
-                               const int64_t* shard_offsets, int32_t* d_out_ids, float* d_out_dists, void* stream) {
+                               int64_t shard_stride, const int64_t* shard_offsets, int32_t* d_out_ids, float* d_out_dists,
+                               void* stream) {
   return guard([&] {
     if (!d_ids || !d_dists || !d_out_ids || !d_out_dists) fail(HNSWB200_EINVAL, "merge_topk: NULL argument");
     if (n_shards < 1 || n_shards > 32) fail(HNSWB200_EINVAL, "merge_topk: n_shards must be in 1..32");
     if (nq <= 0 || k <= 0) fail(HNSWB200_EINVAL, "merge_topk: nq and k must be > 0");
+    if (shard_stride == 0) shard_stride = nq * k;
+    if (shard_stride < nq * k) fail(HNSWB200_EINVAL, "merge_topk: shard_stride smaller than nq * k");
     hb::ShardOffsets offs{};
     for (int s = 0; s < n_shards; s++) {
       int64_t o = shard_offsets ? shard_offsets[s] : 0;
@@ -158,7 +161,7 @@ int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n
     }
     int wpb = 8;
     hb::merge_topk_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        d_ids, d_dists, n_shards, nq, k, offs, d_out_ids, d_out_dists);
+        d_ids, d_dists, n_shards, nq, k, shard_stride, offs, d_out_ids, d_out_dists);
     CUDA_CHECK(cudaGetLastError());
     if (!stream) CUDA_CHECK(cudaStreamSynchronize(0));
   });

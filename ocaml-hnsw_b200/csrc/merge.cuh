@@ -11,13 +11,13 @@ namespace hb {
 
 struct ShardOffsets { int32_t v[32]; };   // global id = shard-local id + v[shard]
 
-__global__ void merge_topk_kernel(const int32_t* ids, const float* dists, int S, int64_t nq, int k,
+__global__ void merge_topk_kernel(const int32_t* ids, const float* dists, int S, int64_t nq, int k, int64_t shard_stride,
                                   ShardOffsets offs, int32_t* out_ids, float* out_dists) {
   int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (q >= nq) return;
   int head = 0;
-  const size_t base = lane < S ? ((size_t)lane * nq + q) * k : 0;
+  const size_t base = lane < S ? (size_t)lane * shard_stride + (size_t)q * k : 0;
   for (int j = 0; j < k; j++) {
     uint64_t key = KEY_INF;
     float myd = 0.f;

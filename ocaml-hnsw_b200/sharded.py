@@ -66,9 +66,11 @@ class ShardedHgraph:
         key = (nq, k)
         if key not in self._buf:
             dev = torch.device("cuda", self.local.info().device)
+            # one packed block per rank: [0] = ids (int32), [1] = distances (fp32 bits) -> ONE all-gather
+            packed = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
             self._buf = {key: dict(
-                ids=torch.empty((nq, k), dtype=torch.int32, device=dev),
-                d=torch.empty((nq, k), dtype=torch.float32, device=dev),
+                packed=packed, ids=packed[0], d=packed[1].view(torch.float32),
+                gathered=torch.empty((self.world, 2, nq, k), dtype=torch.int32, device=dev),
                 out_ids=torch.empty((nq, k), dtype=torch.int32, device=dev),
                 out_d=torch.empty((nq, k), dtype=torch.float32, device=dev))}
         return self._buf[key]
@@ -85,10 +87,11 @@ class ShardedHgraph:
                                  stream=stream, mode=mode)
         if self.world == 1:
             return b["ids"], b["d"]
-        all_ids = gather_rows(b["ids"], self.world, self.group)
-        all_d = gather_rows(b["d"], self.world, self.group)
-        capi.check(capi.lib().hnswb200_merge_topk_device(all_ids.data_ptr(), all_d.data_ptr(), self.world, nq, k,
-                                                         capi.ptr(self.offsets), b["out_ids"].data_ptr(),
+        import torch.distributed as dist
+        g = b["gathered"]
+        dist.all_gather_into_tensor(g.view(self.world * 2, nq, k), b["packed"], group=self.group)
+        capi.check(capi.lib().hnswb200_merge_topk_device(g.data_ptr(), g.data_ptr() + nq * k * 4, self.world, nq, k,
+                                                         2 * nq * k, capi.ptr(self.offsets), b["out_ids"].data_ptr(),
                                                          b["out_d"].data_ptr(), stream or None))
         return b["out_ids"], b["out_d"]
 

@@ -60,6 +60,30 @@ def test_bruteforce_pads_when_k_exceeds_n():
     _same_up_to_ties(ids_g, d_g, ids_o, d_o)
 
 
+def test_merge_topk_packed_blocks():
+    """The layout of the single all-gather: every shard contributes one [ids | dists] block."""
+    import torch
+    rng = np.random.default_rng(10)
+    S, nq, k = 3, 50, 7
+    d = np.sort(rng.random((S, nq, k), dtype=np.float32), axis=2)
+    ids = rng.integers(0, 1000, (S, nq, k)).astype(np.int32)
+    packed = np.stack([ids, d.view(np.int32)], axis=1)             # [S][2][nq][k]
+    t = torch.from_numpy(np.ascontiguousarray(packed)).cuda()
+    o_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    o_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    offs = np.arange(S, dtype=np.int64) * 1000
+    capi.check(capi.lib().hnswb200_merge_topk_device(t.data_ptr(), t.data_ptr() + nq * k * 4, S, nq, k, 2 * nq * k,
+                                                     capi.ptr(offs), o_ids.data_ptr(), o_d.data_ptr(), None))
+    got = o_ids.cpu().numpy()
+    for q in range(nq):
+        cand = sorted((d[s, q, j], ids[s, q, j] + offs[s]) for s in range(S) for j in range(k))
+        assert got[q].tolist() == [c[1] for c in cand[:k]]
+    with pytest.raises(ValueError, match="shard_stride"):
+        capi.check(capi.lib().hnswb200_merge_topk_device(t.data_ptr(), t.data_ptr(), S, nq, k, 3, None, o_ids.data_ptr(),
+                                                         o_d.data_ptr(), None))
+
+
 def test_bruteforce_integer_data_is_exact():
     rng = np.random.default_rng(5)
     X = rng.integers(0, 219, (4000, 128)).astype(np.float32)
@@ -83,7 +107,7 @@ def test_merge_topk():
     o_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
     offs = np.arange(S, dtype=np.int64) * (1 << 20)                # shard s holds global rows [s * 2^20, ...)
-    capi.check(capi.lib().hnswb200_merge_topk_device(t_ids.data_ptr(), t_d.data_ptr(), S, nq, k, capi.ptr(offs),
+    capi.check(capi.lib().hnswb200_merge_topk_device(t_ids.data_ptr(), t_d.data_ptr(), S, nq, k, 0, capi.ptr(offs),
                                                      o_ids.data_ptr(), o_d.data_ptr(), None))
     got_ids, got_d = o_ids.cpu().numpy(), o_d.cpu().numpy()
     for q in range(nq):
