@@ -366,7 +366,7 @@ def run_ours(a):
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": round(rec_star, 4), "mode": "parity",
-                       "sharding": f"{world} row shards, all-gather + merge" if world > 1 else "single index",
+                       "sharding": f"{world} row shards, exchange: {sh.exchange}, then merge kernel" if world > 1 else "single index",
                        "l2": "index (vectors + adjacency) larger than L2; no flush between steps",
                        "ef_sweep": sweep},
             "build_seconds": build_s, "ground_truth_seconds": gt_s,

@@ -148,6 +148,14 @@ int hnswb200_search(hnswb200_index* idx, const float* queries, int64_t nq, int k
 int hnswb200_search_device(hnswb200_index* idx, const float* d_queries, int64_t nq, int k, int ef,
                            int mode, int32_t* d_ids, float* d_dists, void* stream);
 
+/* Multi-GPU variant: the result rows are stored into `n_out` (1..8) destinations, each `[nq][k]`,
+ * any of which may be peer-mapped memory of another GPU (symmetric memory over NVLink): every
+ * rank writes its block straight into every peer's gather buffer, so no all-gather follows the
+ * search — only a barrier and hnswb200_merge_topk_device. */
+int hnswb200_search_device_multi(hnswb200_index* idx, const float* d_queries, int64_t nq, int k, int ef,
+                                 int mode, int n_out, int32_t* const* d_ids_list,
+                                 float* const* d_dists_list, void* stream);
+
 /* Per-query work counters of the last search call: uint32[nq][3] = n_dist, n_exp0, n_expU. */
 int hnswb200_last_search_counters(hnswb200_index* idx, uint32_t* out, int64_t nq);
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "hnswb200_insert": (_i32, [_vp, _vp, _i64, _vp]),
     "hnswb200_search": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "hnswb200_search_device": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hnswb200_search_device_multi": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hnswb200_last_search_counters": (_i32, [_vp, _vp, _i64]),
     "hnswb200_import_graph": (_i32, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "hnswb200_export_layer": (_i32, [_vp, _i32, _i32, _vp, _vp, C.POINTER(_i64)]),

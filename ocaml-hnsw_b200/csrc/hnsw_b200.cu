@@ -269,7 +269,8 @@ void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
 }
 
 void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
-                   int32_t* d_ids, float* d_dists, cudaStream_t s, bool own_stream) {
+                   int32_t* d_ids, float* d_dists, cudaStream_t s, bool own_stream, int n_peer = 0,
+                   int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr) {
   if (nq < 0 || k <= 0) fail(HNSWB200_EINVAL, "search: nq must be >= 0 and k > 0");
   if (ef < k) fail(HNSWB200_EINVAL, "search: ef must be >= k");
   if (mode != HNSWB200_MODE_PARITY && mode != HNSWB200_MODE_FAST) fail(HNSWB200_EINVAL, "search: unknown mode");
@@ -291,6 +292,8 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp;
   p.out_ids = d_ids; p.out_dists = d_dists; p.counters = x->d_counters.p;
+  p.n_peer_out = n_peer;
+  for (int r = 0; r < n_peer; r++) { p.peer_ids[r] = peer_ids[r]; p.peer_dists[r] = peer_dists[r]; }
   p.next_query = x->d_next.p; p.bitset_pool = x->d_bitpool.p; p.pool_busy = x->d_pool_busy.p;
   p.pool_size = x->pool_size; p.words = x->pool_words; p.events = x->d_events.p;
   CUDA_CHECK(cudaEventRecord(x->ev0, s));
@@ -507,6 +510,21 @@ int hnswb200_search_device(hnswb200_index* x, const float* d_queries, int64_t nq
     use_device(x);
     cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
     search_device(x, d_queries, nq, k, ef, mode, d_ids, d_dists, s, stream == nullptr);
+  });
+}
+
+int hnswb200_search_device_multi(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode, int n_out,
+                                 int32_t* const* d_ids_list, float* const* d_dists_list, void* stream) {
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    if (n_out < 1 || n_out > 8 || !d_ids_list || !d_dists_list) fail(HNSWB200_EINVAL, "search_device_multi: 1..8 destinations");
+    for (int r = 0; r < n_out; r++) if (!d_ids_list[r] || !d_dists_list[r]) fail(HNSWB200_EINVAL, "search_device_multi: NULL destination");
+    if (nq > 0 && !d_queries) fail(HNSWB200_EINVAL, "search_device_multi: queries is NULL");
+    if (x->ld != x->dim) fail(HNSWB200_EINVAL, "search_device: dim must be a multiple of 4 (rows are read with 128-bit loads)");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
+    search_device(x, d_queries, nq, k, ef, mode, nullptr, nullptr, s, stream == nullptr, n_out, d_ids_list, d_dists_list);
   });
 }
 

@@ -36,6 +36,11 @@ struct SearchParams {
   int smem_per_warp;
   int32_t* out_ids;          // [nq][k] or null
   float* out_dists;          // [nq][k]
+  // multi-GPU: the same result rows are also stored straight into every peer's gathered block
+  // (peer-mapped device memory over NVLink), replacing the all-gather that would follow
+  int n_peer_out;
+  int32_t* peer_ids[8];
+  float* peer_dists[8];
   uint32_t* counters;        // [nq][3]
   unsigned int* next_query;  // work counter
   uint32_t* bitset_pool;     // [pool_size][words]
@@ -414,7 +419,11 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
         od = g.metric == 0 ? (float)sqrt((double)d) : d;   // Float.sqrt in double, fp32 store (:889,:899)
       }
       if (p.out_ids) p.out_ids[(size_t)qi * p.k + i] = oid;
-      p.out_dists[(size_t)qi * p.k + i] = od;
+      if (p.out_dists) p.out_dists[(size_t)qi * p.k + i] = od;
+      for (int r = 0; r < p.n_peer_out; r++) {
+        p.peer_ids[r][(size_t)qi * p.k + i] = oid;
+        p.peer_dists[r][(size_t)qi * p.k + i] = od;
+      }
     }
     if (lane == 0) {
       if (p.counters) {

@@ -3,9 +3,12 @@
 The reference has nothing distributed; this is the sharding BASELINE.json's
 north_star prescribes on top of the same `Ohnsw` entry points: every rank builds and searches
 the HNSW sub-graph of its own rows `[lo, hi)`, the query batch is the same on every rank, and
-the per-shard `[nq][k]` result rows are exchanged with ONE all-gather (NCCL over NVLink) and
-merged by `hnswb200_merge_topk_device` (shard-local ids become global ids inside the merge).
-No collective runs during graph traversal or during the build.
+the per-shard `[nq][k]` result rows are exchanged and merged by `hnswb200_merge_topk_device`
+(shard-local ids become global ids inside the merge).  The exchange is fused into the search
+kernel: every rank's warps store their finished rows straight into every peer's gather buffer
+(torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so what follows the search is one
+device-side barrier and the merge — no all-gather.  Where symmetric memory is unavailable the
+exchange is ONE packed NCCL all-gather.  No collective runs during graph traversal or the build.
 
 torch is plumbing here: device buffers for the exchange and `torch.distributed`.
 """
@@ -41,10 +44,13 @@ class ShardedHgraph:
     """`Ohnsw.Hgraph` over a row-sharded dataset.  `n_total` rows exist across the group; this rank
     owns `shard_range(n_total, rank, world)`."""
 
-    def __init__(self, local, n_total, rank, world, group=None):
+    def __init__(self, local, n_total, rank, world, group=None, peer_exchange=True):
         self.local, self.n_total, self.rank, self.world, self.group = local, int(n_total), rank, world, group
         self.offsets = shard_offsets(n_total, world)
         self._buf = {}
+        self.peer_exchange = peer_exchange and world > 1     # False: packed NCCL all-gather
+        self.exchange = "none" if world == 1 else None       # set on first use: "peer-store" | "nccl-all-gather"
+        self._step = 0
 
     @staticmethod
     def build(distance, local_rows, n_total, *, num_connections, num_nodes_search_construction, rank=0, world=1,
@@ -61,11 +67,39 @@ class ShardedHgraph:
         capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(local_rows), local_rows.shape[0], capi.ptr(lv)))
         return ShardedHgraph(h, n_total, rank, world, group)
 
+    def _peer_buffers(self, nq, k, dev):
+        """Two gather buffers [world][2][nq][k] in symmetric memory (double buffered: a rank may start
+        writing step i+2 only after the barrier of step i+1, by which every rank has merged step i)."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        out = []
+        for _ in range(2):
+            t = symm_mem.empty((self.world, 2, nq, k), dtype=torch.int32, device=dev)
+            hdl = symm_mem.rendezvous(t, group)
+            block = 2 * nq * k * 4
+            ids_ptrs = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.rank * block for r in range(self.world)])
+            d_ptrs = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.rank * block + nq * k * 4 for r in range(self.world)])
+            out.append(dict(t=t, hdl=hdl, ids_ptrs=ids_ptrs, d_ptrs=d_ptrs))
+        return out
+
     def _buffers(self, nq, k):
         import torch
         key = (nq, k)
         if key not in self._buf:
             dev = torch.device("cuda", self.local.info().device)
+            peer = None
+            if self.peer_exchange and self.world <= 8:
+                try:
+                    peer = self._peer_buffers(nq, k, dev)
+                    self.exchange = "peer-store"
+                except Exception as e:                      # no symmetric memory on this system / build
+                    self.exchange = f"nccl-all-gather (symmetric memory unavailable: {type(e).__name__})"
+            elif self.world > 1:
+                self.exchange = "nccl-all-gather"
+            self._peer = peer
             # one packed block per rank: [0] = ids (int32), [1] = distances (fp32 bits) -> ONE all-gather
             packed = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
             self._buf = {key: dict(
@@ -83,13 +117,24 @@ class ShardedHgraph:
         nq = q_dev.shape[0]
         b = self._buffers(nq, k)
         stream = torch.cuda.current_stream().cuda_stream
-        self.local.search_device(q_dev.data_ptr(), nq, k, k if ef is None else ef, b["ids"].data_ptr(), b["d"].data_ptr(),
-                                 stream=stream, mode=mode)
         if self.world == 1:
+            self.local.search_device(q_dev.data_ptr(), nq, k, k if ef is None else ef, b["ids"].data_ptr(), b["d"].data_ptr(),
+                                     stream=stream, mode=mode)
             return b["ids"], b["d"]
         import torch.distributed as dist
-        g = b["gathered"]
-        dist.all_gather_into_tensor(g.view(self.world * 2, nq, k), b["packed"], group=self.group)
+        if self._peer is not None:
+            # fused exchange: the search kernel stores every finished row into all peers' buffers
+            pb = self._peer[self._step & 1]
+            self._step += 1
+            capi.check(capi.lib().hnswb200_search_device_multi(self.local._h, q_dev.data_ptr(), nq, k, k if ef is None else ef,
+                                                               mode, self.world, pb["ids_ptrs"], pb["d_ptrs"], stream or None))
+            pb["hdl"].barrier(channel=0)
+            g = pb["t"]
+        else:
+            self.local.search_device(q_dev.data_ptr(), nq, k, k if ef is None else ef, b["ids"].data_ptr(), b["d"].data_ptr(),
+                                     stream=stream, mode=mode)
+            g = b["gathered"]
+            dist.all_gather_into_tensor(g.view(self.world * 2, nq, k), b["packed"], group=self.group)
         capi.check(capi.lib().hnswb200_merge_topk_device(g.data_ptr(), g.data_ptr() + nq * k * 4, self.world, nq, k,
                                                          2 * nq * k, capi.ptr(self.offsets), b["out_ids"].data_ptr(),
                                                          b["out_d"].data_ptr(), stream or None))
