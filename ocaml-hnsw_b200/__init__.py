@@ -10,8 +10,8 @@ from . import _capi as capi
 from . import ohnsw as Ohnsw
 from . import hnsw as Hnsw
 from . import graphio
-from .dataset import Dataset, Recall, brute_force_knn_l2, sift_like
-from .graphio import FlatGraph, read_graph, write_graph
+from .dataset import Dataset, Recall, brute_force_knn_l2, read_fbin, sift_like, write_fbin
+from .graphio import FlatGraph, read_graph, to_dot, write_graph
 
 __all__ = ["capi", "Ohnsw", "Hnsw", "Dataset", "Recall", "brute_force_knn_l2", "sift_like", "graphio",
-           "FlatGraph", "read_graph", "write_graph"]
+           "FlatGraph", "read_graph", "write_graph", "to_dot", "read_fbin", "write_fbin"]

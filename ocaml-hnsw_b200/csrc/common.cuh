@@ -101,6 +101,20 @@ __device__ __forceinline__ float team_reduce(float2 acc2) {
   acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
   return acc;
 }
+// Two team sums with three shuffles instead of six: in the first butterfly step each lane keeps
+// one of the two values (lanes 0-3 of the team the first, lanes 4-7 the second) and sends the
+// other, so the remaining two steps reduce one value per lane.  Every partial sum is formed from
+// the same pair of operands as in team_reduce, so the results are bit-identical; value 0 ends in
+// team lanes 0-3, value 1 in lanes 4-7.
+__device__ __forceinline__ float team_reduce2(float2 a2, float2 b2, int tl) {
+  const float a = __fadd_rn(a2.x, a2.y), b = __fadd_rn(b2.x, b2.y);
+  const bool upper = (tl & 4) != 0;
+  const float send = upper ? a : b, keep = upper ? b : a;
+  float acc = __fadd_rn(keep, __shfl_xor_sync(FULL, send, 4));
+  acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 2));
+  acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, 1));
+  return acc;
+}
 __device__ __forceinline__ float finish_metric(float acc, int metric) {
   return metric == 0 ? acc : (metric == 1 ? __fsub_rn(1.0f, acc) : -acc);
 }
@@ -163,8 +177,13 @@ __device__ __forceinline__ void team_dist(const GraphView& g, const float4* q, c
       }
     }
   }
+  if (NV == 2) {
+    const float r = finish_metric(team_reduce2(acc[0], acc[NV - 1], tl), g.metric);
+    out[0] = r; out[NV - 1] = r;                 // out[0] is valid in team lanes 0-3, out[1] in lanes 4-7
+  } else {
 #pragma unroll
-  for (int v = 0; v < NV; v++) out[v] = finish_metric(team_reduce(acc[v]), g.metric);
+    for (int v = 0; v < NV; v++) out[v] = finish_metric(team_reduce(acc[v]), g.metric);
+  }
 }
 
 // ids[0..cnt) (shared) -> d[0..cnt) (shared).  cnt >= 1 is warp-uniform.  Rounds of eight
@@ -179,10 +198,8 @@ __device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, 
     const int node[2] = {(int)ids[j0], (int)ids[min(j1, cnt - 1)]};
     float o[2];
     team_dist<CPL, 2>(g, q, qs, node, tl, o);
-    if (tl == 0) {
-      d[j0] = o[0];
-      if (j1 < cnt) d[j1] = o[1];
-    }
+    if (tl == 0) d[j0] = o[0];
+    if (tl == 4 && j1 < cnt) d[j1] = o[1];
   }
   if (base < cnt) {
     const int j0 = base + team;

@@ -24,12 +24,42 @@ class Dataset:
         self.test_ids = test_ids
 
     @staticmethod
+    def read(train_fbin, test_fbin, k, limit_train=None, limit_test=None, device=0):
+        """Dataset.read (benchmark/dataset.ml:76-102) over .fbin files; the ground-truth distances are
+        recomputed with the exact GPU scan (the reference takes them from the HDF5 `distances` set)."""
+        train, test = read_fbin(train_fbin, limit_train), read_fbin(test_fbin, limit_test)
+        ids, d = brute_force_knn_l2(train, test, k, device, return_ids=True)
+        return Dataset(train, test, d, test_ids=ids)
+
+    @staticmethod
     def random(dim, num_train, num_test, k, seed=(1234, 4321), device=0):
         """Dataset.random (benchmark/dataset.ml:47-58): Lacaml.S.Mat.random = uniform [-1, 1)."""
         train = (np.random.default_rng(seed[0]).random((num_train, dim), dtype=np.float32) * 2 - 1)
         test = (np.random.default_rng(seed[1]).random((num_test, dim), dtype=np.float32) * 2 - 1)
         ids, d = brute_force_knn_l2(train, test, k, device, return_ids=True)
         return Dataset(train, test, d, test_ids=ids)
+
+
+def write_fbin(path, a):
+    """Raw vector file: int32 n, int32 dim, then n x dim float32 (the big-ann-benchmarks .fbin layout).
+    The reference reads ann-benchmarks HDF5 (benchmark/dataset.ml:76-102); this image has no HDF5
+    library, so real data sets come in through this format (scripts/hdf5_to_fbin.py converts where
+    h5py exists)."""
+    a = np.ascontiguousarray(a, np.float32)
+    with open(path, "wb") as f:
+        np.array(a.shape, np.int32).tofile(f)
+        a.tofile(f)
+
+
+def read_fbin(path, max_rows=None):
+    with open(path, "rb") as f:
+        n, dim = np.fromfile(f, np.int32, 2).tolist()
+        if max_rows is not None:
+            n = min(n, max_rows)
+        a = np.fromfile(f, np.float32, n * dim)
+    if a.size != n * dim:
+        raise ValueError("truncated .fbin file")
+    return a.reshape(n, dim)
 
 
 def sift_like(n, dim, latent=16, seed=1234, noise=0.05, proj_seed=99):

@@ -64,3 +64,27 @@ def read_graph(path):
         rest = np.fromfile(f, np.float32)
         vectors = rest.reshape(n, dim) if rest.size == n * dim else None
     return FlatGraph(n, max_layer, entry, offs, nbrs, levels), dict(dim=dim, M=M, id_base=id_base), vectors
+
+
+def to_dot(g, layer=0, positions=None, highlight=None):
+    """Graphviz dump of one layer (test/test.ml:6-56 show_hgraph / show_neighbours): nodes, one
+    undirected edge per symmetric link, optional 2-D positions and a highlighted node set."""
+    out = ["graph hnsw {", "  node [shape=circle, fontsize=8];"]
+    o, a = g.offsets[layer], g.nbrs[layer]
+    present = [i for i in range(g.n) if layer == 0 or (g.levels is not None and g.levels[i] >= layer) or o[i + 1] > o[i]]
+    hl = set(highlight or [])
+    for i in present:
+        attrs = []
+        if positions is not None:
+            attrs.append(f'pos="{float(positions[i][0]):.3f},{float(positions[i][1]):.3f}!"')
+        if i in hl:
+            attrs.append('color=red')
+        if i == g.entry:
+            attrs.append('shape=doublecircle')
+        out.append(f"  {i} [{', '.join(attrs)}];" if attrs else f"  {i};")
+    for i in present:
+        for j in a[o[i]:o[i + 1]].tolist():
+            if i < j:
+                out.append(f"  {i} -- {j};")
+    out.append("}")
+    return "\n".join(out)

@@ -80,3 +80,17 @@ def test_graph_file_roundtrip(tmp_path):
     assert (g2.n, g2.max_layer, g2.entry, meta["dim"], meta["M"]) == (3, 1, 2, 2, 3)
     assert g2.row(0, 1).tolist() == [0, 2] and np.array_equal(v2, vec) and g2.levels.tolist() == [0, 0, 1]
     assert g2.is_symmetric(0)
+
+
+def test_fbin_roundtrip_and_dot(tmp_path):
+    a = np.random.default_rng(0).random((37, 5), dtype=np.float32)
+    H.write_fbin(tmp_path / "x.fbin", a)
+    assert np.array_equal(H.read_fbin(tmp_path / "x.fbin"), a)
+    assert H.read_fbin(tmp_path / "x.fbin", max_rows=10).shape == (10, 5)
+    g = H.FlatGraph(3, 0, 1, [np.array([0, 1, 3, 4])], [np.array([1, 0, 2, 1], np.int32)], np.zeros(3, np.int32))
+    dot = H.to_dot(g, 0, positions=[(0, 0), (1, 0), (2, 0)], highlight=[2])
+    assert "0 -- 1;" in dot and "1 -- 2;" in dot and dot.count("--") == 2 and "doublecircle" in dot
+    p = tmp_path / "g.bin"
+    H.write_graph(p, g, dim=5, M=2, vectors=a[:3])
+    g2, meta, vec = H.read_graph(p)
+    assert g2.entry == 1 and meta["dim"] == 5 and np.array_equal(vec, a[:3]) and np.array_equal(g2.nbrs[0], g.nbrs[0])

@@ -169,3 +169,26 @@ def test_import_validation():
     bad = H.FlatGraph(3, 0, 0, [np.array([0, 1, 1, 1])], [np.array([9], np.int32)])
     with pytest.raises(ValueError, match="out of range"):
         h.import_graph(X, bad)
+
+
+def test_search_device_multi_writes_every_destination(uni2k):
+    """hnswb200_search_device_multi (the fused multi-GPU exchange): the same result rows land in
+    every destination block; here all destinations are local buffers."""
+    import ctypes as C
+    import torch
+    X, Q, o, h = uni2k
+    nq, k, ef = len(Q), 10, 40
+    ids_o, d_o = o.search(Q, k, ef)
+    q = torch.from_numpy(Q).cuda()
+    blocks = torch.full((3, 2, nq, k), -7, dtype=torch.int32, device="cuda")
+    ids_ptrs = (C.c_void_p * 3)(*[blocks[r, 0].data_ptr() for r in range(3)])
+    d_ptrs = (C.c_void_p * 3)(*[blocks[r, 1].data_ptr() for r in range(3)])
+    torch.cuda.synchronize()
+    capi.check(capi.lib().hnswb200_search_device_multi(h._h, q.data_ptr(), nq, k, ef, capi.MODE_PARITY, 3, ids_ptrs, d_ptrs, None))
+    torch.cuda.synchronize()
+    got = blocks.cpu().numpy()
+    for r in range(3):
+        assert np.array_equal(got[r, 0], ids_o)
+        assert np.array_equal(got[r, 1].view(np.uint32), d_o.view(np.uint32))
+    with pytest.raises(ValueError, match="destinations"):
+        capi.check(capi.lib().hnswb200_search_device_multi(h._h, q.data_ptr(), nq, k, ef, capi.MODE_PARITY, 9, ids_ptrs, d_ptrs, None))
