@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--n", "--rows", type=int, default=1_000_000, dest="n")
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--M", type=int, default=16)
