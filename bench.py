@@ -315,7 +315,7 @@ def run_ours(a):
         ids, d = Ohnsw.knn_batch_bigarray(h, Q, k=a.k, ef=ef_star)       # own stream: events bracket the kernel alone
         st = h.stats()
         kms.append(st.search_kernel_ms)
-        abytes = st.search_algorithmic_bytes + a.nq * (4.0 * a.dim + 8.0 * a.k)
+        abytes = st.search_algorithmic_bytes          # counted: n_dist*4*dim + rows*4*slots + nq*(4*dim + 8*k)
     peak, peak_src = measured_peak()
     k_ms = statistics.mean(kms)
     achieved = abytes / (k_ms * 1e-3) / 1e9

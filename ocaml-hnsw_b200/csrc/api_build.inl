@@ -351,6 +351,17 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   }
   int64_t done = n_old;
   if (done == 0) { x->entry = 0; x->max_layer = 0; done = 1; x->n = 1; }     // :774-778
+  // if a batch fails the index keeps the nodes linked so far: drop the bookkeeping of the rest
+  auto rollback = [&]() {
+    x->h_level.resize((size_t)x->n);
+    x->h_upper_off.resize((size_t)x->n);
+    int64_t rows_kept = 0;
+    for (int64_t i = 0; i < x->n; i++) rows_kept += x->h_level[(size_t)i];
+    x->h_row_owner.resize((size_t)rows_kept);
+    x->rowsU = rows_kept;
+    x->layer_stats_dirty = true;
+  };
+  try {
   while (done < n_tot) {
     int64_t B = std::max<int64_t>(1, std::min<int64_t>(max_batch, done / ratio));
     B = std::min<int64_t>(B, n_tot - done);
@@ -365,6 +376,7 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
     x->n = done;
   }
   CUDA_CHECK(cudaStreamSynchronize(s));
+  } catch (...) { rollback(); throw; }
   unsigned long long c[4];
   CUDA_CHECK(cudaMemcpy(c, x->b_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
   unsigned long long evs[2];

@@ -111,6 +111,7 @@ struct hnswb200_index {
   // stats
   hnswb200_stats st{};
   int64_t last_nq = 0;
+  int last_k = 0;
   std::mutex mu;
 
   hb::GraphView view() const {
@@ -307,6 +308,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   CUDA_CHECK(cudaEventRecord(x->ev1, s));
   x->st.gpu_launches += 1;
   x->last_nq = nq;
+  x->last_k = k;
   x->st.search_queries = (uint64_t)nq;
   if (own_stream) {
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -606,7 +608,8 @@ int hnswb200_get_stats(hnswb200_index* x, hnswb200_stats* out) {
     }
     // lib/hnsw.ml:732-751 counts distance calls; bytes per SURVEY.md 8d
     st.search_algorithmic_bytes = (double)st.search_n_dist * 4.0 * x->dim + (double)st.search_n_exp0 * 4.0 * x->slots0 +
-                                  (double)st.search_n_expU * 4.0 * x->slotsU;
+                                  (double)st.search_n_expU * 4.0 * x->slotsU +
+                                  (double)x->last_nq * (4.0 * x->dim + 8.0 * x->last_k);
     // Hgraph.Stats (lib/hnsw.ml:353-375); recomputed only after the graph changed
     st.num_layers = x->n ? x->max_layer + 1 : 0;
     for (int l = 0; x->layer_stats_dirty && l < st.num_layers && l < 16; l++) {
