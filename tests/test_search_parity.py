@@ -192,3 +192,20 @@ def test_search_device_multi_writes_every_destination(uni2k):
         assert np.array_equal(got[r, 1].view(np.uint32), d_o.view(np.uint32))
     with pytest.raises(ValueError, match="destinations"):
         capi.check(capi.lib().hnswb200_search_device_multi(h._h, q.data_ptr(), nq, k, ef, capi.MODE_PARITY, 9, ids_ptrs, d_ptrs, None))
+
+
+def test_config_c1_benchmark_ml_shape():
+    """BASELINE.json configs[0] / SURVEY.md C1 — the reference's own CPU-runnable case
+    (benchmark/benchmark.ml shape): 10k x 128 uniform [-1,1), M=16, efConstruction=100, "~k:50, keep
+    10" (Q4).  Search parity on the oracle-built graph, and the literal recipe's first 10 queries."""
+    X, Q = uniform(10000, 128, 1234), uniform(1000, 128, 4321)
+    o = _oracle_index(X, 16, 100)
+    h = _gpu_from(o, X, 16, 100)
+    ids, d = _check(o, h, Q, 10, 50)
+    _check(o, h, Q[:10], 10, 10)                              # benchmark.ml: num_test = 10, ~k:10
+    gt = O.bruteforce(X, Q, 10)[0]
+    assert 0.5 < H.Recall.ids(gt, ids) < 0.9                  # ~0.67 at ef=50 on uniform data
+    hb = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=16, num_nodes_search_construction=100,
+                                    levels=draw_levels(len(X), 16))
+    ids_b, _ = Ohnsw.knn_batch_bigarray(hb, Q, k=10, ef=50)
+    assert H.Recall.ids(gt, ids_b) >= H.Recall.ids(gt, ids) - 0.005
