@@ -115,7 +115,9 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
 /* Tunables (0 = automatic): "hash_slots" (visited hash slots per query), "visited_mode" (1 = shared
  * memory hash, 2 = global bitset), "warps_per_cta", "max_warps_per_sm", "build_batch" (max inserts
  * per GPU batch, default 16384; 1 = sequential inserts), "build_ratio" (a batch is at most
- * n / build_ratio nodes, default 64). */
+ * n / build_ratio nodes, default 64), "host_chunks" (2..4: hnswb200_search cuts batches of >= 4096
+ * queries into that many pieces on separate streams so the copies run under the search; off by
+ * default — on B200 the extra launches cost what the overlap saves). */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
 int hnswb200_destroy(hnswb200_index* idx);
 

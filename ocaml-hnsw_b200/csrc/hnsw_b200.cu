@@ -92,6 +92,9 @@ struct hnswb200_index {
   std::vector<int32_t> h_upper_off;
   // scratch
   cudaStream_t stream = nullptr;
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // host-buffer search: copy / compute overlap
+  cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t param_host_chunks = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
   DevBuf<int32_t> d_ids;
@@ -269,44 +272,64 @@ void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
   }
 }
 
-void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
-                   int32_t* d_ids, float* d_dists, cudaStream_t s, bool own_stream, int n_peer = 0,
-                   int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr) {
+void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
   if (nq < 0 || k <= 0) fail(HNSWB200_EINVAL, "search: nq must be >= 0 and k > 0");
   if (ef < k) fail(HNSWB200_EINVAL, "search: ef must be >= k");
   if (mode != HNSWB200_MODE_PARITY && mode != HNSWB200_MODE_FAST) fail(HNSWB200_EINVAL, "search: unknown mode");
   if (x->n == 0 || x->entry < 0) fail(HNSWB200_EINVAL, "knn: empty hgraph");     // lib/ohnsw.ml:862
   if (ef > 4096) fail(HNSWB200_EINVAL, "search: ef > 4096 is not supported");
-  if (nq == 0) return;
-  SearchPlan pl = plan_search(x, ef, nq);
-  ensure_pool(x, pl.grid * pl.warps, x->n);
-  if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));   // one set per warp
-  x->d_counters.reserve((size_t)nq * 3);
-  x->d_next.reserve(1);
-  x->d_events.reserve(2);
-  CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, sizeof(unsigned int), s));
-  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
+}
+
+// One launch of the search kernel over `nq` queries; counters / work counter are the caller's.
+void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_queries, int64_t nq, int k, int ef,
+                    int32_t* d_ids, float* d_dists, uint32_t* counters, unsigned int* next, cudaStream_t s,
+                    int n_peer = 0, int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr) {
   hb::SearchParams p;
   p.g = x->view();
   p.queries = d_queries; p.nq = nq; p.ef = ef; p.k = k; p.ef_cap = pl.ef_cap;
   p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp;
-  p.out_ids = d_ids; p.out_dists = d_dists; p.counters = x->d_counters.p;
+  p.out_ids = d_ids; p.out_dists = d_dists; p.counters = counters;
   p.n_peer_out = n_peer;
   for (int r = 0; r < n_peer; r++) { p.peer_ids[r] = peer_ids[r]; p.peer_dists[r] = peer_dists[r]; }
-  p.next_query = x->d_next.p; p.bitset_pool = x->d_bitpool.p; p.pool_busy = x->d_pool_busy.p;
+  p.next_query = next; p.bitset_pool = x->d_bitpool.p; p.pool_busy = x->d_pool_busy.p;
   p.pool_size = x->pool_size; p.words = x->pool_words; p.events = x->d_events.p;
-  CUDA_CHECK(cudaEventRecord(x->ev0, s));
+  SearchPlan q = pl;
+  q.grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (nq + pl.warps - 1) / pl.warps));
   switch (pl.cpl) {
-    case 1: launch_search<1>(p, pl, s); break;
-    case 2: launch_search<2>(p, pl, s); break;
-    case 3: launch_search<3>(p, pl, s); break;
-    case 4: launch_search<4>(p, pl, s); break;
-    default: launch_search<0>(p, pl, s); break;
+    case 1: launch_search<1>(p, q, s); break;
+    case 2: launch_search<2>(p, q, s); break;
+    case 3: launch_search<3>(p, q, s); break;
+    case 4: launch_search<4>(p, q, s); break;
+    default: launch_search<0>(p, q, s); break;
   }
-  CUDA_CHECK(cudaEventRecord(x->ev1, s));
   x->st.gpu_launches += 1;
+}
+
+void finish_search(hnswb200_index* x, const unsigned long long* evs, int mode) {
+  x->st.search_visited_overflows = evs[0];
+  if (evs[1] && mode == HNSWB200_MODE_PARITY)
+    fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
+                             std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
+}
+
+void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
+                   int32_t* d_ids, float* d_dists, cudaStream_t s, bool own_stream, int n_peer = 0,
+                   int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr) {
+  check_search_args(x, nq, k, ef, mode);
+  if (nq == 0) return;
+  SearchPlan pl = plan_search(x, ef, nq);
+  ensure_pool(x, pl.grid * pl.warps, x->n);
+  if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));   // one set per warp
+  x->d_counters.reserve((size_t)nq * 3);
+  x->d_next.reserve(8);
+  x->d_events.reserve(2);
+  CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, sizeof(unsigned int), s));
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
+  CUDA_CHECK(cudaEventRecord(x->ev0, s));
+  enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists);
+  CUDA_CHECK(cudaEventRecord(x->ev1, s));
   x->last_nq = nq;
   x->last_k = k;
   x->st.search_queries = (uint64_t)nq;
@@ -314,11 +337,62 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
     CUDA_CHECK(cudaStreamSynchronize(s));
     unsigned long long evs[2];
     CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
-    x->st.search_visited_overflows = evs[0];
-    if (evs[1] && mode == HNSWB200_MODE_PARITY)
-      fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
-                               std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
+    finish_search(x, evs, mode);
   }
+}
+
+// Ohnsw.knn_batch_bigarray with host buffers: H2D of the queries, search, D2H of the rows.
+// Optionally ("host_chunks" >= 2) a large batch is cut into pieces on separate streams so the
+// copies of one piece run under the search of another; measured on B200 this does not pay
+// (10k queries: 1.41 ms in one piece, 1.41-1.57 ms in 2-4), so it is off by default.
+// search_kernel_ms then spans first kernel start to last kernel end.
+constexpr int HOST_CHUNKS = 4;
+void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int ef, int mode, int32_t* ids, float* dists) {
+  check_search_args(x, nq, k, ef, mode);
+  if (nq == 0) return;
+  SearchPlan pl = plan_search(x, ef, nq);
+  ensure_pool(x, pl.grid * pl.warps, x->n);
+  if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));
+  // the global-bitset mode gives every warp of ONE launch its own set: no concurrent launches there
+  int C = x->param_host_chunks >= 2 ? (int)std::min<int64_t>(x->param_host_chunks, HOST_CHUNKS) : 1;
+  if (pl.hash_slots == 0 || nq < 4096) C = 1;
+  x->d_q.reserve((size_t)nq * x->ld);
+  x->d_ids.reserve((size_t)nq * k);
+  x->d_dists.reserve((size_t)nq * k);
+  x->d_counters.reserve((size_t)nq * 3);
+  x->d_next.reserve(8);
+  x->d_events.reserve(2);
+  cudaStream_t s0 = x->stream;
+  if (C > 1 && !x->aux_stream[0]) {
+    for (int c = 0; c < HOST_CHUNKS - 1; c++) CUDA_CHECK(cudaStreamCreateWithFlags(&x->aux_stream[c], cudaStreamNonBlocking));
+    for (int c = 0; c < HOST_CHUNKS; c++) CUDA_CHECK(cudaEventCreateWithFlags(&x->aux_event[c], cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, 8 * sizeof(unsigned int), s0));
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s0));
+  if (C > 1) {
+    CUDA_CHECK(cudaEventRecord(x->aux_event[0], s0));
+    for (int c = 1; c < C; c++) CUDA_CHECK(cudaStreamWaitEvent(x->aux_stream[c - 1], x->aux_event[0], 0));
+  }
+  unsigned long long evs[2];
+  for (int c = 0; c < C; c++) {
+    const int64_t q0 = nq * c / C, q1 = nq * (c + 1) / C, m = q1 - q0;
+    cudaStream_t sc = c == 0 ? s0 : x->aux_stream[c - 1];
+    upload_rows(x->d_q.p + (size_t)q0 * x->ld, x->ld, queries + (size_t)q0 * x->dim, x->dim, m, sc);
+    if (c == 0) CUDA_CHECK(cudaEventRecord(x->ev0, s0));
+    enqueue_search(x, pl, x->d_q.p + (size_t)q0 * x->ld, m, k, ef, x->d_ids.p + (size_t)q0 * k, x->d_dists.p + (size_t)q0 * k,
+                   x->d_counters.p + (size_t)q0 * 3, x->d_next.p + c, sc);
+    if (ids) CUDA_CHECK(cudaMemcpyAsync(ids + (size_t)q0 * k, x->d_ids.p + (size_t)q0 * k, (size_t)m * k * 4, cudaMemcpyDeviceToHost, sc));
+    CUDA_CHECK(cudaMemcpyAsync(dists + (size_t)q0 * k, x->d_dists.p + (size_t)q0 * k, (size_t)m * k * 4, cudaMemcpyDeviceToHost, sc));
+    if (c > 0) CUDA_CHECK(cudaEventRecord(x->aux_event[c], sc));
+  }
+  for (int c = 1; c < C; c++) CUDA_CHECK(cudaStreamWaitEvent(s0, x->aux_event[c], 0));
+  CUDA_CHECK(cudaEventRecord(x->ev1, s0));
+  CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost, s0));
+  x->last_nq = nq;
+  x->last_k = k;
+  x->st.search_queries = (uint64_t)nq;
+  CUDA_CHECK(cudaStreamSynchronize(s0));
+  finish_search(x, evs, mode);
 }
 
 // ---- import / export ----------------------------------------------------------------------------------
@@ -460,6 +534,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "build_ratio") x->param_build_ratio = value;
     else if (s == "max_warps_per_sm") x->param_max_warps_per_sm = value;
     else if (s == "visited_mode") x->param_visited_mode = value;
+    else if (s == "host_chunks") x->param_host_chunks = value;
     else fail(HNSWB200_EINVAL, "unknown parameter: " + s);
   });
 }
@@ -471,6 +546,8 @@ int hnswb200_destroy(hnswb200_index* x) {
     if (x->stream) cudaStreamSynchronize(x->stream);
     if (x->ev0) cudaEventDestroy(x->ev0);
     if (x->ev1) cudaEventDestroy(x->ev1);
+    for (cudaStream_t a : x->aux_stream) if (a) cudaStreamDestroy(a);
+    for (cudaEvent_t e : x->aux_event) if (e) cudaEventDestroy(e);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
   });
@@ -482,23 +559,7 @@ int hnswb200_search(hnswb200_index* x, const float* queries, int64_t nq, int k, 
     if (nq > 0 && (!queries || !dists)) fail(HNSWB200_EINVAL, "search: queries/dists is NULL");
     std::lock_guard<std::mutex> lk(x->mu);
     use_device(x);
-    if (x->n == 0 || x->entry < 0) fail(HNSWB200_EINVAL, "knn: empty hgraph");
-    if (nq <= 0) { if (nq < 0) fail(HNSWB200_EINVAL, "search: nq < 0"); return; }
-    if (k <= 0) fail(HNSWB200_EINVAL, "search: k must be > 0");
-    x->d_q.reserve((size_t)nq * x->ld);
-    x->d_ids.reserve((size_t)nq * k);
-    x->d_dists.reserve((size_t)nq * k);
-    upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, x->stream);
-    search_device(x, x->d_q.p, nq, k, ef, mode, x->d_ids.p, x->d_dists.p, x->stream, false);
-    if (ids) CUDA_CHECK(cudaMemcpyAsync(ids, x->d_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, x->stream));
-    CUDA_CHECK(cudaMemcpyAsync(dists, x->d_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, x->stream));
-    unsigned long long evs[2];
-    CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost, x->stream));
-    CUDA_CHECK(cudaStreamSynchronize(x->stream));
-    x->st.search_visited_overflows = evs[0];
-    if (evs[1] && mode == HNSWB200_MODE_PARITY)
-      fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
-                               std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
+    search_host(x, queries, nq, k, ef, mode, ids, dists);
   });
 }
 

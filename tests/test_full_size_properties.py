@@ -52,6 +52,10 @@ def test_idempotent_and_buffer_kinds_agree(full):
     a = Ohnsw.knn_batch_bigarray(h, Q, k=K, ef=41)
     b = Ohnsw.knn_batch_bigarray(h, Q, k=K, ef=41)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    h.set_param("host_chunks", 3)                 # copy / search overlap in three pieces: same bytes
+    c = Ohnsw.knn_batch_bigarray(h, Q, k=K, ef=41)
+    h.set_param("host_chunks", 1)
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1].view(np.uint32), c[1].view(np.uint32))
     q = torch.from_numpy(Q).cuda()
     ids = torch.empty((NQ, K), dtype=torch.int32, device="cuda")
     d = torch.empty((NQ, K), dtype=torch.float32, device="cuda")
