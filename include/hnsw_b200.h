@@ -102,6 +102,7 @@ typedef struct hnswb200_stats {
   double   layer_mean_degree[16];
   int64_t  layer_isolated[16];
   uint64_t build_visited_overflows;  /* inserts whose visited set left shared memory */
+  uint64_t search_tie_overflows;     /* queries with more than 32 evicted candidates tied at the beam's top distance */
 } hnswb200_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -117,7 +118,9 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
  * per GPU batch, default 16384; 1 = sequential inserts), "build_ratio" (a batch is at most
  * n / build_ratio nodes, default 64), "host_chunks" (2..4: hnswb200_search cuts batches of >= 4096
  * queries into that many pieces on separate streams so the copies run under the search; off by
- * default — on B200 the extra launches cost what the overlap saves). */
+ * default — on B200 the extra launches cost what the overlap saves), "strict_ties" (1: a PARITY
+ * search fails when a query had more than 32 evicted candidates tied at the beam's top distance —
+ * heavy duplicate vectors — instead of only counting it in hnswb200_stats.search_tie_overflows). */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
 int hnswb200_destroy(hnswb200_index* idx);
 

@@ -94,7 +94,7 @@ struct hnswb200_index {
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // host-buffer search: copy / compute overlap
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
-  int64_t param_host_chunks = 0;
+  int64_t param_host_chunks = 0, param_strict_ties = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
   DevBuf<int32_t> d_ids;
@@ -309,7 +309,11 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
 
 void finish_search(hnswb200_index* x, const unsigned long long* evs, int mode) {
   x->st.search_visited_overflows = evs[0];
-  if (evs[1] && mode == HNSWB200_MODE_PARITY)
+  x->st.search_tie_overflows = evs[1];
+  // More than TIES_CAP evicted candidates at exactly the beam's top distance (many duplicate
+  // vectors): the surplus is not revisited.  The reference's own order among equal keys is
+  // unspecified (Core_kernel.Heap), so this is reported, and only an error on request.
+  if (evs[1] && mode == HNSWB200_MODE_PARITY && x->param_strict_ties)
     fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
                              std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
 }
@@ -535,6 +539,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "max_warps_per_sm") x->param_max_warps_per_sm = value;
     else if (s == "visited_mode") x->param_visited_mode = value;
     else if (s == "host_chunks") x->param_host_chunks = value;
+    else if (s == "strict_ties") x->param_strict_ties = value;
     else fail(HNSWB200_EINVAL, "unknown parameter: " + s);
   });
 }

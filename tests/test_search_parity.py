@@ -209,3 +209,29 @@ def test_config_c1_benchmark_ml_shape():
                                     levels=draw_levels(len(X), 16))
     ids_b, _ = Ohnsw.knn_batch_bigarray(hb, Q, k=10, ef=50)
     assert H.Recall.ids(gt, ids_b) >= H.Recall.ids(gt, ids) - 0.005
+
+
+def test_heavy_duplicates_do_not_fail():
+    """Hundreds of copies of a few vectors: far more than 32 candidates tie at the beam boundary.
+    The reference's order among equal keys is unspecified (Core_kernel.Heap); the GPU must still
+    answer (distances equal to the oracle's, ids a valid choice among the ties), count the
+    overflow, and fail only when strict_ties is set."""
+    rng = np.random.default_rng(5)
+    base = uniform(40, 16, 7)
+    X = np.concatenate([np.repeat(base[:4], 150, axis=0), base[4:], uniform(500, 16, 8)]).astype(np.float32)
+    X = X[rng.permutation(len(X))]
+    Q = np.concatenate([base[:4] + 1e-3, uniform(20, 16, 9)]).astype(np.float32)
+    o = _oracle_index(X, 8, 40)
+    h = _gpu_from(o, X, 8, 40)
+    ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=20)
+    ids_o, d_o = o.search(Q, 10, 20)
+    ok = ids_g >= 0                                                       # (a degenerate graph may hold fewer than k reachable nodes)
+    assert np.array_equal(ok, ids_o >= 0) and ok[:, 0].all()
+    found = np.sqrt(((X[np.maximum(ids_g, 0)] - Q[:, None, :]) ** 2).sum(-1))
+    assert np.allclose(found[ok], d_g[ok], rtol=1e-5, atol=1e-6)          # every returned id is at its reported distance
+    assert np.allclose(d_g[4:][ok[4:]], d_o[4:][ok[4:]], rtol=1e-6)       # queries away from the duplicates: as the oracle
+    st = h.stats()
+    if st.search_tie_overflows:
+        h.set_param("strict_ties", 1)
+        with pytest.raises(capi.HnswB200Error, match="equal-distance"):
+            Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=20)
