@@ -71,8 +71,8 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   int splits = std::max(1, std::min(32, (8 * num_sms + qblocks - 1) / qblocks));       // >= ~8 waves of CTAs
   int64_t split_len = ((n + splits - 1) / splits + hb::TC_N - 1) / hb::TC_N * hb::TC_N;
   splits = (int)((n + split_len - 1) / split_len);
-  partial.reserve((size_t)splits * nq * hb::TC_KP);
-  bound.reserve((size_t)splits * nq);
+  partial.reserve((size_t)splits * hb::TC_HALVES * nq * hb::TC_KP);
+  bound.reserve((size_t)splits * hb::TC_HALVES * nq);
   hb::TcParams p{};
   p.x_hi = x_hi.p; p.x_lo = x_lo.p; p.q_hi = q_hi.p; p.q_lo = q_lo.p; p.x_norm = x_norm.p;
   p.n = n; p.nq = nq; p.kp = kp; p.segs = any_lo ? 3 : 1; p.split_len = split_len; p.partial = partial.p; p.bound = bound.p;
@@ -85,7 +85,7 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
 
   hb::TcFinishParams f{};
   f.g.vec = d_data; f.g.ld4 = ld / 4; f.g.chunks = ld / 4; f.g.metric = 0; f.g.n = (int)n;
-  f.queries = d_q; f.partial = partial.p; f.bound = bound.p; f.S = splits; f.nq = nq; f.k = k; f.k_cap = round_up(k, 32);
+  f.queries = d_q; f.partial = partial.p; f.bound = bound.p; f.S = splits * hb::TC_HALVES; f.nq = nq; f.k = k; f.k_cap = round_up(k, 32);
   f.q_chunks = round_up(ld / 4, 2);
   f.smem_per_warp = hb::tc_finish_smem_per_warp(f.k_cap, f.q_chunks);
   f.eps = any_lo ? 1.0f / 4096.0f : 1.0f / 65536.0f;

@@ -28,7 +28,8 @@ constexpr int TC_N = 256;        // data rows per accumulator  (UMMA N)
 constexpr int TC_KC = 64;        // bf16 elements per k-chunk: 128 bytes per row, four K=16 MMAs
 constexpr int TC_STAGES = 3;
 constexpr int TC_KP = 16;        // candidates kept per query per split (shorter sorted lists: the epilogue is the bottleneck)
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;   // 8 warps: warps w and w+4 share accumulator rows 32(w%4).., each takes half the columns
+constexpr int TC_HALVES = TC_THREADS / 128;
 constexpr int TC_A_BYTES = TC_M * TC_KC * 2;
 constexpr int TC_B_BYTES = TC_N * TC_KC * 2;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -50,8 +51,8 @@ struct TcParams {
   int kp;
   int segs;                    // 1: hi.hi only (inputs exactly bf16); 3: hi.hi + lo.hi + hi.lo
   int64_t split_len;           // data rows per gridDim.y slice (multiple of TC_N)
-  uint64_t* partial;           // [gridDim.y][nq][TC_KP] keys (approximate distance, id)
-  float* bound;                // [gridDim.y][nq] approximate distance below which nothing was rejected
+  uint64_t* partial;           // [gridDim.y * TC_HALVES][nq][TC_KP] keys (approximate distance, id)
+  float* bound;                // [gridDim.y * TC_HALVES][nq] approximate distance below which nothing was rejected
 };
 
 __host__ __device__ inline size_t tc_smem_bytes() {
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_STAGES + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = (warp & 3) * 32 + (tid & 31), half = warp >> 2;     // accumulator row (= TMEM lane) and column half of this thread
   const int64_t q0 = (int64_t)blockIdx.x * TC_M;
   const int64_t x_begin = (int64_t)blockIdx.y * p.split_len;
   const int64_t x_end = min(p.n, x_begin + p.split_len);
@@ -240,20 +242,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
         if (cnt == TC_KP) thr = key_dist(my_list[TC_KP - 1]);
       };
 #pragma unroll 1
-      for (int cb = 0; cb < TC_N / 32; cb++) {
+      for (int cb = half * (TC_N / 32 / TC_HALVES); cb < (half + 1) * (TC_N / 32 / TC_HALVES); cb++) {
         uint32_t r[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), r);
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32), r);
         const float4* xn4 = reinterpret_cast<const float4*>(xn + cb * 32);
+        // fast path: does ANY of the 32 columns beat the threshold?  (two instructions per value,
+        // no branch; after the first tiles the answer is almost always no)
+        float dd[32];
+        bool any = false;
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
-          const float4 nv = xn4[j4];
-          const float nn[4] = {nv.x, nv.y, nv.z, nv.w};
+          const float4 nv = xn4[j4];                                        // columns past the end carry +inf norms
+          dd[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(r[j4 * 4 + 0]), nv.x);
+          dd[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(r[j4 * 4 + 1]), nv.y);
+          dd[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(r[j4 * 4 + 2]), nv.z);
+          dd[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(r[j4 * 4 + 3]), nv.w);
+          any |= (dd[j4 * 4 + 0] < thr) | (dd[j4 * 4 + 1] < thr) | (dd[j4 * 4 + 2] < thr) | (dd[j4 * 4 + 3] < thr);
+        }
+        if (any) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int j = j4 * 4 + u, col = cb * 32 + j;
-            const float d = fmaf(-2.f, __uint_as_float(r[j]), nn[u]);     // columns past the end carry +inf norms
-            if (d < thr) {
-              my_stage[ns++] = make_key(d, (uint32_t)(xb + col));
+          for (int j = 0; j < 32; j++) {
+            if (dd[j] < thr) {
+              my_stage[ns++] = make_key(dd[j], (uint32_t)(xb + cb * 32 + j));
               if (ns == TC_STAGE_CAP) flush();
             }
           }
@@ -267,10 +277,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
   }
 
   // partial lists and the rejection bound of this split
-  if (q0 + tid < p.nq) {
-    uint64_t* out = p.partial + ((size_t)blockIdx.y * p.nq + (q0 + tid)) * TC_KP;
+  if (q0 + row < p.nq) {
+    const size_t slot = ((size_t)blockIdx.y * TC_HALVES + half) * p.nq + (q0 + row);
+    uint64_t* out = p.partial + slot * TC_KP;
     for (int j = 0; j < TC_KP; j++) out[j] = j < cnt ? my_list[j] : KEY_INF;
-    p.bound[(size_t)blockIdx.y * p.nq + (q0 + tid)] = thr;       // +inf while fewer than TC_KP were seen
+    p.bound[slot] = thr;                                         // +inf while fewer than TC_KP were seen
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
