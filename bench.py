@@ -51,11 +51,31 @@ def parse():
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--ref-n", type=int, default=100_000, help="--impl reference: rows the CPU build covers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--metric", default="l2", choices=["l2", "angular"],
+                    help="angular = SURVEY.md config C3 (GloVe shape): unit-norm Gaussian-mixture vectors, distance 1 - a.b")
     return ap.parse_args()
 
 
 def workload_name(a):
+    if a.metric == "angular":
+        return f"unit-norm gaussian-mixture {a.n}x{a.dim} fp32 angular, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
     return f"sift-like {a.n}x{a.dim} fp32 L2, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
+
+
+def make_data(a, n, seed):
+    """The synthetic generators of SURVEY.md section 8d: (b) SIFT-like for L2, a unit-norm Gaussian
+    mixture (256 centres, sigma 0.35) for the angular config."""
+    import ocaml_hnsw_b200.dataset as D
+    if a.metric == "l2":
+        return D.sift_like(n, a.dim, seed=seed)
+    centres = np.random.default_rng(99).standard_normal((256, a.dim)).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, a.dim), np.float32)
+    for s in range(0, n, 1 << 18):
+        m = min(1 << 18, n - s)
+        x = centres[rng.integers(0, 256, m)] + 0.35 * rng.standard_normal((m, a.dim)).astype(np.float32)
+        out[s:s + m] = x / np.linalg.norm(x, axis=1, keepdims=True)
+    return out
 
 
 def draw_levels(n, M, seed):
@@ -141,14 +161,15 @@ def run_reference(a):
     from oracle import oracle as O
     threads = O.lib().orc_num_threads()
     n = min(a.ref_n, a.n)
-    X = np.ascontiguousarray(D.sift_like(a.n, a.dim, seed=1234)[:n])      # a true prefix of the GPU arm's dataset
-    Q = D.sift_like(a.nq, a.dim, seed=4321)
+    X = np.ascontiguousarray(make_data(a, a.n, 1234)[:n])                 # a true prefix of the GPU arm's dataset
+    Q = make_data(a, a.nq, 4321)
+    om = O.METRIC_L2 if a.metric == "l2" else O.METRIC_ANGULAR
     lv = draw_levels(n, a.M, 7)
     t0 = time.time()
-    o = O.VecOracle(a.dim).build(X, a.M, a.efc, lv)
+    o = O.VecOracle(a.dim, om).build(X, a.M, a.efc, lv)
     build_s = time.time() - t0
     gt_n = min(a.nq, 2000)
-    gt, _ = O.bruteforce(X, Q[:gt_n], a.k)
+    gt, _ = O.bruteforce(X, Q[:gt_n], a.k, om)
     def recall_at(ef):
         ids = o.search_mt(Q[:gt_n], a.k, ef)[0]
         return float(np.mean([len(set(g.tolist()) & set(i[i >= 0].tolist())) / a.k for g, i in zip(gt, ids)]))
@@ -224,14 +245,15 @@ def run_ours(a):
 
     # ---- synthetic inputs (every rank generates the same arrays, then keeps its rows)
     lo, hi = shard_range(a.n, rank, world)
-    X = H.sift_like(a.n, a.dim, seed=1234)[lo:hi].copy()
-    Q = H.sift_like(a.nq, a.dim, seed=4321)
+    X = make_data(a, a.n, 1234)[lo:hi].copy()
+    Q = make_data(a, a.nq, 4321)
+    metric = Ohnsw.distance_l2 if a.metric == "l2" else Ohnsw.distance_angular
     lv = draw_levels(hi - lo, a.M, 7 + rank)
 
     # ---- index build (outside the timed search region; reported as build seconds)
     barrier()
     t0 = time.perf_counter()
-    sh = ShardedHgraph.build(Ohnsw.distance_l2, X, a.n, num_connections=a.M, num_nodes_search_construction=a.efc,
+    sh = ShardedHgraph.build(metric, X, a.n, num_connections=a.M, num_nodes_search_construction=a.efc,
                              rank=rank, world=world, levels=lv, device=local_rank)
     torch.cuda.synchronize()
     build_s = max_over_ranks(time.perf_counter() - t0)
@@ -240,7 +262,7 @@ def run_ours(a):
 
     # ---- exact ground truth with the brute-force kernel (per shard, merged like the search results)
     t0 = time.perf_counter()
-    gt_ids_l, gt_d_l = H.brute_force_knn_l2(X, Q, a.k, device=local_rank, return_ids=True)
+    gt_ids_l, gt_d_l = H.brute_force_knn_l2(X, Q, a.k, device=local_rank, return_ids=True, metric=metric)
     gt_s = time.perf_counter() - t0
     if world > 1:
         gi = gather_rows(torch.from_numpy(gt_ids_l).to(dev), world)
@@ -348,7 +370,7 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle as O
         g = h.export_graph()
-        o = O.VecOracle(a.dim)
+        o = O.VecOracle(a.dim, O.METRIC_L2 if a.metric == "l2" else O.METRIC_ANGULAR)
         o.import_graph(X, O.Graph(g.n, g.max_layer, g.entry, g.offsets, g.nbrs, g.levels))
         threads = O.lib().orc_num_threads()
         o.search_mt(Q[:1000], a.k, ef_star)
