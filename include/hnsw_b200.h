@@ -120,7 +120,9 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
  * queries into that many pieces on separate streams so the copies run under the search; off by
  * default — on B200 the extra launches cost what the overlap saves), "strict_ties" (1: a PARITY
  * search fails when a query had more than 32 evicted candidates tied at the beam's top distance —
- * heavy duplicate vectors — instead of only counting it in hnswb200_stats.search_tie_overflows). */
+ * heavy duplicate vectors — instead of only counting it in hnswb200_stats.search_tie_overflows),
+ * "row_floats" (stride of a vector row in floats, a multiple of 4 >= dim; default dim rounded up to
+ * 4; only on an empty index). */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
 int hnswb200_destroy(hnswb200_index* idx);
 
@@ -147,7 +149,7 @@ int hnswb200_insert(hnswb200_index* idx, const float* data, int64_t n, const int
 int hnswb200_search(hnswb200_index* idx, const float* queries, int64_t nq, int k, int ef, int mode,
                     int32_t* ids, float* dists);
 
-/* Same, all buffers already in this index's device memory: queries `float[nq][dim]` dense,
+/* Same, all buffers already in this index's device memory: queries `float[nq][dim]` dense (any dim),
  * outputs `[nq][k]`.  `stream` is a cudaStream_t (NULL = the index's own stream; the call then
  * synchronises before returning, otherwise it only enqueues). */
 int hnswb200_search_device(hnswb200_index* idx, const float* d_queries, int64_t nq, int k, int ef,

@@ -272,6 +272,17 @@ void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
   }
 }
 
+// Device-resident queries are dense [nq][dim]; when rows are padded (ld != dim) they are re-laid
+// into the index's own padded buffer first (one strided device-to-device copy).
+const float* padded_queries(hnswb200_index* x, const float* d_queries, int64_t nq, cudaStream_t s) {
+  if (x->ld == x->dim || nq == 0) return d_queries;
+  x->d_q.reserve((size_t)nq * x->ld);
+  CUDA_CHECK(cudaMemsetAsync(x->d_q.p, 0, (size_t)nq * x->ld * sizeof(float), s));
+  CUDA_CHECK(cudaMemcpy2DAsync(x->d_q.p, (size_t)x->ld * sizeof(float), d_queries, (size_t)x->dim * sizeof(float),
+                               (size_t)x->dim * sizeof(float), (size_t)nq, cudaMemcpyDeviceToDevice, s));
+  return x->d_q.p;
+}
+
 void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
   if (nq < 0 || k <= 0) fail(HNSWB200_EINVAL, "search: nq must be >= 0 and k > 0");
   if (ef < k) fail(HNSWB200_EINVAL, "search: ef must be >= k");
@@ -540,6 +551,11 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "visited_mode") x->param_visited_mode = value;
     else if (s == "host_chunks") x->param_host_chunks = value;
     else if (s == "strict_ties") x->param_strict_ties = value;
+    else if (s == "row_floats") {             // vector row stride in floats (multiple of 4, >= dim); only on an empty index
+      if (x->n != 0) fail(HNSWB200_EINVAL, "row_floats can only be set on an empty index");
+      if (value < x->dim || value % 4 != 0) fail(HNSWB200_EINVAL, "row_floats must be a multiple of 4 and >= dim");
+      x->ld = (int)value;
+    }
     else fail(HNSWB200_EINVAL, "unknown parameter: " + s);
   });
 }
@@ -573,11 +589,10 @@ int hnswb200_search_device(hnswb200_index* x, const float* d_queries, int64_t nq
   return guard([&] {
     if (!x) fail(HNSWB200_EINVAL, "index is NULL");
     if (nq > 0 && (!d_queries || !d_dists)) fail(HNSWB200_EINVAL, "search_device: queries/dists is NULL");
-    if (x->ld != x->dim) fail(HNSWB200_EINVAL, "search_device: dim must be a multiple of 4 (rows are read with 128-bit loads)");
     std::lock_guard<std::mutex> lk(x->mu);
     use_device(x);
     cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
-    search_device(x, d_queries, nq, k, ef, mode, d_ids, d_dists, s, stream == nullptr);
+    search_device(x, padded_queries(x, d_queries, nq, s), nq, k, ef, mode, d_ids, d_dists, s, stream == nullptr);
   });
 }
 
@@ -588,11 +603,10 @@ int hnswb200_search_device_multi(hnswb200_index* x, const float* d_queries, int6
     if (n_out < 1 || n_out > 8 || !d_ids_list || !d_dists_list) fail(HNSWB200_EINVAL, "search_device_multi: 1..8 destinations");
     for (int r = 0; r < n_out; r++) if (!d_ids_list[r] || !d_dists_list[r]) fail(HNSWB200_EINVAL, "search_device_multi: NULL destination");
     if (nq > 0 && !d_queries) fail(HNSWB200_EINVAL, "search_device_multi: queries is NULL");
-    if (x->ld != x->dim) fail(HNSWB200_EINVAL, "search_device: dim must be a multiple of 4 (rows are read with 128-bit loads)");
     std::lock_guard<std::mutex> lk(x->mu);
     use_device(x);
     cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
-    search_device(x, d_queries, nq, k, ef, mode, nullptr, nullptr, s, stream == nullptr, n_out, d_ids_list, d_dists_list);
+    search_device(x, padded_queries(x, d_queries, nq, s), nq, k, ef, mode, nullptr, nullptr, s, stream == nullptr, n_out, d_ids_list, d_dists_list);
   });
 }
 

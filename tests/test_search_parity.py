@@ -235,3 +235,25 @@ def test_heavy_duplicates_do_not_fail():
         h.set_param("strict_ties", 1)
         with pytest.raises(capi.HnswB200Error, match="equal-distance"):
             Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=20)
+
+
+def test_device_queries_with_padded_rows():
+    """Device-resident queries are dense [nq][dim] even when the index pads its rows (dim = 6 -> 8
+    floats, or an explicit row_floats): same rows as the host-buffer call."""
+    import torch
+    X, Q = uniform(800, 6, 51), uniform(40, 6, 52)
+    lv = draw_levels(len(X), 4)
+    for rf in (0, 32):
+        h = Ohnsw.Hgraph(6, capi.L2, 4, 30)
+        if rf:
+            h.set_param("row_floats", rf)
+        capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), len(X), capi.ptr(lv)))
+        ids_h, d_h = Ohnsw.knn_batch_bigarray(h, Q, k=5, ef=20)
+        q = torch.from_numpy(Q).cuda()
+        ids = torch.empty((40, 5), dtype=torch.int32, device="cuda")
+        d = torch.empty((40, 5), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        h.search_device(q.data_ptr(), 40, 5, 20, ids.data_ptr(), d.data_ptr())
+        assert np.array_equal(ids.cpu().numpy(), ids_h) and np.array_equal(d.cpu().numpy().view(np.uint32), d_h.view(np.uint32))
+    with pytest.raises(ValueError, match="row_floats"):
+        h.set_param("row_floats", 64)                      # not on a built index
