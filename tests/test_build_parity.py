@@ -131,6 +131,25 @@ def test_sequential_gpu_build_is_the_oracle_graph(kind, n, dim, M, efC):
     assert h.stats().build_n_dist >= o.counters()[0] * 0.9
 
 
+def test_committed_fixture_build_and_search(golden_dir):
+    """tests/golden/oracle_small.npz: the sequential GPU build reproduces the frozen graph, and the GPU
+    search on it the frozen rows and work counters."""
+    import os
+    f = np.load(os.path.join(golden_dir, "oracle_small.npz"))
+    M, efC, k, ef = f["params"].tolist()
+    X, Q = f["X"], f["Q"]
+    h = Ohnsw.Hgraph(X.shape[1], Ohnsw.distance_l2, M, efC)
+    h.set_param("build_batch", 1)
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), len(X), capi.ptr(np.ascontiguousarray(f["levels"], np.int32))))
+    g = h.export_graph()
+    assert (g.entry, g.max_layer) == (int(f["entry"]), int(f["max_layer"]))
+    for l in range(g.max_layer + 1):
+        assert np.array_equal(g.offsets[l], f[f"offsets{l}"]) and np.array_equal(g.nbrs[l], f[f"nbrs{l}"])
+    ids, d = Ohnsw.knn_batch_bigarray(h, Q, k=k, ef=ef)
+    assert np.array_equal(ids, f["ids"]) and np.array_equal(d.view(np.uint32), f["dists"].view(np.uint32))
+    assert np.array_equal(h.last_search_counters(len(Q)).astype(np.uint64), f["counters"])
+
+
 def test_build_is_deterministic():
     X = uniform(6000, 64, 5)
     lv = draw_levels(len(X), 8)

@@ -146,3 +146,21 @@ def test_insert_then_knn_1d():
     assert h.max_layer() == 2 and h.entry_point() == 2
     assert h.adjacent(1, 2) == [] and h.adjacent(2, 2) == []
     assert [n for n, _ in h.knn(15.1, 2)] == [15, 16]
+
+
+def test_oracle_reproduces_committed_fixture(golden_dir):
+    """tests/golden/oracle_small.npz (made by tests/golden/make_oracle_fixture.py): the oracle's build
+    and search on a small seeded data set, frozen."""
+    import os
+    import numpy as np
+    from oracle import oracle as O
+    f = np.load(os.path.join(golden_dir, "oracle_small.npz"))
+    M, efC, k, ef = f["params"].tolist()
+    o = O.VecOracle(f["X"].shape[1]).build(f["X"], M, efC, f["levels"])
+    g = o.export()
+    assert (g.entry, g.max_layer) == (int(f["entry"]), int(f["max_layer"]))
+    for l in range(g.max_layer + 1):
+        assert np.array_equal(g.offsets[l], f[f"offsets{l}"]) and np.array_equal(g.nbrs[l], f[f"nbrs{l}"])
+    ids, d, cnt = o.search(f["Q"], k, ef, counters=True)
+    assert np.array_equal(ids, f["ids"]) and np.array_equal(d.view(np.uint32), f["dists"].view(np.uint32))
+    assert np.array_equal(cnt, f["counters"])
