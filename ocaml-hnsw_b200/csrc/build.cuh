@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   w.keys = reinterpret_cast<uint64_t*>(my);
   w.ties = w.keys + p.ef_cap;
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
-  w.newd = reinterpret_cast<float*>(w.newid + 32);
-  w.qs = reinterpret_cast<float4*>(w.newd + 32);
+  w.newd = reinterpret_cast<float*>(w.newid + p.nb_cap);
+  w.qs = reinterpret_cast<float4*>(w.newd + p.nb_cap);
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
   float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);
   uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);

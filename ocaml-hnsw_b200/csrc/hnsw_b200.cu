@@ -160,7 +160,7 @@ void upload_rows(float* dst, int ld, const float* src, int dim, int64_t n, cudaS
 
 // ---- search ---------------------------------------------------------------------------------------
 struct SearchPlan {
-  int cpl, warps, ef_cap, hash_slots, q_chunks, smem_per_warp, grid;
+  int cpl, warps, ef_cap, hash_slots, q_chunks, smem_per_warp, grid, nb_cap;
   size_t smem;
 };
 
@@ -213,7 +213,8 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   // visited hash: ~42 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 42 * ef), 128);
-  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks);
+  pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
+  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap);
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
   hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
   {
@@ -225,7 +226,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   }
   if (use_bitset_visited(x, ef, fixed + hs * 4, x->n)) hs = 0;
   pl.hash_slots = hs;
-  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks);
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks, pl.nb_cap);
   // pack the SM: as many warps as shared memory and registers (64 per thread: 32 warps) allow, in CTAs of <= 4 warps
   int per_sm_warps = std::max(1, std::min(4 * HB_SEARCH_MINB, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 256))));
   if (x->param_max_warps_per_sm > 0) per_sm_warps = std::max(1, std::min<int>(per_sm_warps, (int)x->param_max_warps_per_sm));
@@ -300,7 +301,7 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   p.queries = d_queries; p.nq = nq; p.ef = ef; p.k = k; p.ef_cap = pl.ef_cap;
   p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
-  p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp;
+  p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp; p.nb_cap = pl.nb_cap;
   p.out_ids = d_ids; p.out_dists = d_dists; p.counters = counters;
   p.n_peer_out = n_peer;
   for (int r = 0; r < n_peer; r++) { p.peer_ids[r] = peer_ids[r]; p.peer_dists[r] = peer_dists[r]; }

@@ -32,6 +32,7 @@ struct SearchParams {
   int accept_ties;           // Hnsw.Ba flavour: accept d <= top (lib/hnsw.ml:494-506)
   int pad_inf;               // Hnsw.Ba flavour: +inf padding (lib/hnsw.ml:771)
   int hash_slots;            // multiple of 4
+  int nb_cap;                // list slots gathered per pass: 32 or 64 (staging arrays hold this many)
   int q_smem_chunks;         // float4 slots reserved for the query copy
   int smem_per_warp;
   int32_t* out_ids;          // [nq][k] or null
@@ -50,8 +51,8 @@ struct SearchParams {
   unsigned long long* events; // [0] visited spills, [1] tie-list overflows
 };
 
-__host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, int q_chunks) {
-  return ef_cap * 8 + TIES_CAP * 8 + 32 * 4 + 32 * 4 + q_chunks * 16 + hash_slots * 4;
+__host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, int q_chunks, int nb_cap = 32) {
+  return ef_cap * 8 + TIES_CAP * 8 + nb_cap * 4 + nb_cap * 4 + q_chunks * 16 + hash_slots * 4;
 }
 
 // QREG: the target vector lives in registers (CPL float4 per lane); otherwise in shared memory
@@ -182,36 +183,49 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
     const int32_t* row;
     if (layer == 0) row = g.adj0 + (size_t)c * g.slots0;
     else { int off = g.upper_off[c]; row = off < 0 ? nullptr : g.adjU + ((size_t)off + layer - 1) * g.slotsU; }
-    for (int r0 = 0; r0 < slots && row; r0 += 32) {
-      int nb = (r0 + lane < slots) ? __ldg(row + r0 + lane) : -1;
-      unsigned valid = __ballot_sync(FULL, nb >= 0);
-      if (!valid) break;
-      if (!w.vis.bits && w.vis.count + 32u > w.vis.limit) visited_spill(w.vis, p, lane);
-      bool is_new = nb >= 0 && visited_test_and_set(w.vis, (uint32_t)nb);   // Visited.mem / add (:571-572)
-      unsigned m = __ballot_sync(FULL, is_new);
-      int cnt = __popc(m);
-      w.vis.count += cnt;
-      if (cnt) {
-        if (is_new) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
-        __syncwarp();
+    // Up to nb_cap (32 or 64) list slots are gathered per pass: visited test-and-set chunk by chunk,
+    // ONE batch of distance evaluations for everything new, then acceptance in list order, 32
+    // candidates at a time (rows wider than 32 slots, M > 16, no longer pay a partial round and a
+    // merge per 32-slot chunk).
+    for (int s0 = 0; s0 < slots && row; s0 += p.nb_cap) {
+      int total = 0;
+      bool row_ended = false;
+      for (int r0 = s0; r0 < min(slots, s0 + p.nb_cap); r0 += 32) {
+        int nb = (r0 + lane < slots) ? __ldg(row + r0 + lane) : -1;
+        unsigned valid = __ballot_sync(FULL, nb >= 0);
+        if (!valid) { row_ended = true; break; }
+        if (!w.vis.bits && w.vis.count + 32u > w.vis.limit) visited_spill(w.vis, p, lane);
+        bool is_new = nb >= 0 && visited_test_and_set(w.vis, (uint32_t)nb);   // Visited.mem / add (:571-572)
+        unsigned m = __ballot_sync(FULL, is_new);
+        if (is_new) w.newid[total + __popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
+        total += __popc(m);
+        if (valid != FULL) { row_ended = true; break; }                       // row ended inside this chunk
+      }
+      w.vis.count += total;
+      __syncwarp();
+      if (total) {
         // every vector beyond the first round of eight starts moving towards L2 now, so the
         // later rounds of batch_dist wait for L2, not for HBM
-        if (lane >= 8 && lane < cnt) {
-          const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[lane] * g.ld4 * 16;
-          for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
-        }
-        batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, cnt, lane);          // MinQueue.element (:573)
-        n_dist += cnt;
+        for (int j = lane; j < total; j += 32)
+          if (j >= 8) {
+            const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[j] * g.ld4 * 16;
+            for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
+          }
+        batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, total, lane);        // MinQueue.element (:573)
+        n_dist += total;
+      }
+      for (int g0 = 0; g0 < total; g0 += 32) {
+        const int cnt = min(32, total - g0);
         // ---- accept (:574-578).  The reference takes the candidates one at a time, in list
         // order: accept iff |near| < ef or t < top (t <= top in the Hnsw.Ba flavour), insert, evict
-        // the maximum.  The same decisions for the whole row at once: with U_j = the beam at the
-        // start of the row plus all earlier candidates, top_j is the ef-th smallest distance of
+        // the maximum.  The same decisions for 32 candidates at once: with U_j = the beam at the
+        // start of the group plus all earlier candidates, top_j is the ef-th smallest distance of
         // U_j, so candidate j is accepted iff fewer than ef members of U_j are at distance <= t_j
-        // (< t_j when ties are accepted); the beam after the row is the ef smallest keys of
+        // (< t_j when ties are accepted); the beam after the group is the ef smallest keys of
         // beam + accepted, and an evicted entry stays poppable only while its distance equals
         // the top (stop rule is a strict >, :568).
-        const float t = lane < cnt ? w.newd[lane] : 0.f;
-        const uint64_t key = make_key(t, lane < cnt ? w.newid[lane] : 0u);
+        const float t = lane < cnt ? w.newd[g0 + lane] : 0.f;
+        const uint64_t key = make_key(t, lane < cnt ? w.newid[g0 + lane] : 0u);
         const bool pre = lane < cnt && (n < ef || (p.accept_ties ? t <= top_d : t < top_d));
         const unsigned pm = __ballot_sync(FULL, pre);
         if (pm) {
@@ -287,7 +301,7 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
           }
         }
       }
-      if (valid != FULL) break;                     // row ended inside this round
+      if (row_ended) break;
     }
   }
 }
@@ -372,8 +386,8 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
   w.keys = reinterpret_cast<uint64_t*>(my);
   w.ties = w.keys + p.ef_cap;
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
-  w.newd = reinterpret_cast<float*>(w.newid + 32);
-  w.qs = reinterpret_cast<float4*>(w.newd + 32);
+  w.newd = reinterpret_cast<float*>(w.newid + p.nb_cap);
+  w.qs = reinterpret_cast<float4*>(w.newd + p.nb_cap);
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
 
   while (true) {
