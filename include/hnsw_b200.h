@@ -116,9 +116,10 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
 /* Tunables (0 = automatic): "hash_slots" (visited hash slots per query), "visited_mode" (1 = shared
  * memory hash, 2 = global bitset), "warps_per_cta", "max_warps_per_sm", "build_batch" (max inserts
  * per GPU batch, default 16384; 1 = sequential inserts), "build_ratio" (a batch is at most
- * n / build_ratio nodes, default 64), "host_chunks" (2..4: hnswb200_search cuts batches of >= 4096
- * queries into that many pieces on separate streams so the copies run under the search; off by
- * default — on B200 the extra launches cost what the overlap saves), "strict_ties" (1: a PARITY
+ * n / build_ratio nodes, default 64), "host_chunks" (2..8: hnswb200_search streams batches of
+ * >= 4096 queries to the GPU in this many pieces behind ONE already running search kernel whose
+ * warps wait for the piece that holds their query; default: copy first, then search),
+ * "strict_ties" (1: a PARITY
  * search fails when a query had more than 32 evicted candidates tied at the beam's top distance —
  * heavy duplicate vectors — instead of only counting it in hnswb200_stats.search_tie_overflows),
  * "row_floats" (stride of a vector row in floats, a multiple of 4 >= dim; default dim rounded up to

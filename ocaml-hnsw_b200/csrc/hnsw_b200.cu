@@ -95,6 +95,7 @@ struct hnswb200_index {
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // host-buffer search: copy / compute overlap
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t param_host_chunks = 0, param_strict_ties = 0;
+  unsigned int h_ready[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
   DevBuf<int32_t> d_ids;
@@ -295,8 +296,10 @@ void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
 // One launch of the search kernel over `nq` queries; counters / work counter are the caller's.
 void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_queries, int64_t nq, int k, int ef,
                     int32_t* d_ids, float* d_dists, uint32_t* counters, unsigned int* next, cudaStream_t s,
-                    int n_peer = 0, int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr) {
+                    int n_peer = 0, int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr,
+                    const unsigned int* ready = nullptr, unsigned int ready_step = 1) {
   hb::SearchParams p;
+  p.ready = ready; p.ready_step = ready_step;
   p.g = x->view();
   p.queries = d_queries; p.nq = nq; p.ef = ef; p.k = k; p.ef_cap = pl.ef_cap;
   p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
@@ -340,9 +343,9 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));   // one set per warp
   x->d_counters.reserve((size_t)nq * 3);
   x->d_next.reserve(8);
-  x->d_events.reserve(2);
+  x->d_events.reserve(4);
   CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, sizeof(unsigned int), s));
-  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s));
   CUDA_CHECK(cudaEventRecord(x->ev0, s));
   enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists);
   CUDA_CHECK(cudaEventRecord(x->ev1, s));
@@ -358,56 +361,66 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
 }
 
 // Ohnsw.knn_batch_bigarray with host buffers: H2D of the queries, search, D2H of the rows.
-// Optionally ("host_chunks" >= 2) a large batch is cut into pieces on separate streams so the
-// copies of one piece run under the search of another; measured on B200 this does not pay
-// (10k queries: 1.41 ms in one piece, 1.41-1.57 ms in 2-4), so it is off by default.
-// search_kernel_ms then spans first kernel start to last kernel end.
-constexpr int HOST_CHUNKS = 4;
+// With "host_chunks" = 2..8, batches of >= 4096 queries are streamed (see below;
+// search_kernel_ms then includes the wait for the first piece).  Off by default: measured on
+// B200 it buys 1-2 % of the call (10k queries: 1.204 ms -> 1.185 ms), the copy is already short.
+constexpr int HOST_CHUNKS = 8;
 void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int ef, int mode, int32_t* ids, float* dists) {
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
   SearchPlan pl = plan_search(x, ef, nq);
   ensure_pool(x, pl.grid * pl.warps, x->n);
   if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));
-  // the global-bitset mode gives every warp of ONE launch its own set: no concurrent launches there
   int C = x->param_host_chunks >= 2 ? (int)std::min<int64_t>(x->param_host_chunks, HOST_CHUNKS) : 1;
-  if (pl.hash_slots == 0 || nq < 4096) C = 1;
+  if (nq < 4096) C = 1;
   x->d_q.reserve((size_t)nq * x->ld);
   x->d_ids.reserve((size_t)nq * k);
   x->d_dists.reserve((size_t)nq * k);
   x->d_counters.reserve((size_t)nq * 3);
   x->d_next.reserve(8);
-  x->d_events.reserve(2);
+  x->d_events.reserve(4);
   cudaStream_t s0 = x->stream;
   if (C > 1 && !x->aux_stream[0]) {
-    for (int c = 0; c < HOST_CHUNKS - 1; c++) CUDA_CHECK(cudaStreamCreateWithFlags(&x->aux_stream[c], cudaStreamNonBlocking));
-    for (int c = 0; c < HOST_CHUNKS; c++) CUDA_CHECK(cudaEventCreateWithFlags(&x->aux_event[c], cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&x->aux_stream[0], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&x->aux_event[0], cudaEventDisableTiming));
   }
+  // d_next[0] = work counter, d_next[1] = pieces of the batch copied so far
   CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, 8 * sizeof(unsigned int), s0));
-  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s0));
-  if (C > 1) {
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s0));
+  unsigned long long evs[4];
+  if (C == 1) {
+    upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, s0);
+    CUDA_CHECK(cudaEventRecord(x->ev0, s0));
+    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0);
+  } else {
+    // One kernel, started at once; the queries stream in behind it in C pieces on the copy stream,
+    // each followed by a 4-byte "pieces ready" update the kernel's warps wait on (bounded) before
+    // they read a query of that piece.  The H2D copy is hidden under the search except for piece 0.
+    const unsigned step = (unsigned)((nq + C - 1) / C);
+    cudaStream_t sc = x->aux_stream[0];
     CUDA_CHECK(cudaEventRecord(x->aux_event[0], s0));
-    for (int c = 1; c < C; c++) CUDA_CHECK(cudaStreamWaitEvent(x->aux_stream[c - 1], x->aux_event[0], 0));
+    CUDA_CHECK(cudaStreamWaitEvent(sc, x->aux_event[0], 0));          // counters are zero before any piece lands
+    CUDA_CHECK(cudaEventRecord(x->ev0, s0));
+    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
+                   x->d_next.p + 1, step);
+    for (int c = 0; c < C; c++) {
+      const int64_t q0 = (int64_t)step * c, m = std::min<int64_t>(step, nq - q0);
+      if (m <= 0) break;
+      upload_rows(x->d_q.p + (size_t)q0 * x->ld, x->ld, queries + (size_t)q0 * x->dim, x->dim, m, sc);
+      x->h_ready[c] = (unsigned)(c + 1);
+      CUDA_CHECK(cudaMemcpyAsync(x->d_next.p + 1, &x->h_ready[c], sizeof(unsigned int), cudaMemcpyHostToDevice, sc));
+    }
   }
-  unsigned long long evs[2];
-  for (int c = 0; c < C; c++) {
-    const int64_t q0 = nq * c / C, q1 = nq * (c + 1) / C, m = q1 - q0;
-    cudaStream_t sc = c == 0 ? s0 : x->aux_stream[c - 1];
-    upload_rows(x->d_q.p + (size_t)q0 * x->ld, x->ld, queries + (size_t)q0 * x->dim, x->dim, m, sc);
-    if (c == 0) CUDA_CHECK(cudaEventRecord(x->ev0, s0));
-    enqueue_search(x, pl, x->d_q.p + (size_t)q0 * x->ld, m, k, ef, x->d_ids.p + (size_t)q0 * k, x->d_dists.p + (size_t)q0 * k,
-                   x->d_counters.p + (size_t)q0 * 3, x->d_next.p + c, sc);
-    if (ids) CUDA_CHECK(cudaMemcpyAsync(ids + (size_t)q0 * k, x->d_ids.p + (size_t)q0 * k, (size_t)m * k * 4, cudaMemcpyDeviceToHost, sc));
-    CUDA_CHECK(cudaMemcpyAsync(dists + (size_t)q0 * k, x->d_dists.p + (size_t)q0 * k, (size_t)m * k * 4, cudaMemcpyDeviceToHost, sc));
-    if (c > 0) CUDA_CHECK(cudaEventRecord(x->aux_event[c], sc));
-  }
-  for (int c = 1; c < C; c++) CUDA_CHECK(cudaStreamWaitEvent(s0, x->aux_event[c], 0));
   CUDA_CHECK(cudaEventRecord(x->ev1, s0));
-  CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost, s0));
+  if (ids) CUDA_CHECK(cudaMemcpyAsync(ids, x->d_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
+  CUDA_CHECK(cudaMemcpyAsync(dists, x->d_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
+  CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
   x->last_nq = nq;
   x->last_k = k;
   x->st.search_queries = (uint64_t)nq;
   CUDA_CHECK(cudaStreamSynchronize(s0));
+  if (C > 1) CUDA_CHECK(cudaStreamSynchronize(x->aux_stream[0]));
+  if (evs[2]) fail(HNSWB200_ECUDA, "search: the query copy did not arrive (streamed host buffers)");
   finish_search(x, evs, mode);
 }
 

@@ -48,7 +48,11 @@ struct SearchParams {
   int* pool_busy;
   int pool_size;
   int words;
-  unsigned long long* events; // [0] visited spills, [1] tie-list overflows
+  unsigned long long* events; // [0] visited spills, [1] tie-list overflows, [2] warps that gave up waiting for queries
+  // streamed queries (host-buffer call): the batch arrives in pieces of `ready_step` queries while the
+  // kernel runs; *ready = pieces copied so far (written by the copy stream after each piece)
+  const unsigned int* ready;
+  unsigned int ready_step;
 };
 
 __host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, int q_chunks, int nb_cap = 32) {
@@ -327,7 +331,8 @@ __device__ __forceinline__ void load_target(const GraphView& g, const float4* ro
 // target vector -> shared memory, zero padded to `padded` chunks (the register-free variant)
 __device__ __forceinline__ void load_target_smem(const GraphView& g, const float4* row, float4* qs, int padded, int lane) {
   __syncwarp();
-  for (int ch = lane; ch < padded; ch += 32) qs[ch] = ch < g.chunks ? __ldg(row + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // (__ldcg, not the read-only path: with streamed queries the rows are written while the kernel runs)
+  for (int ch = lane; ch < padded; ch += 32) qs[ch] = ch < g.chunks ? __ldcg(row + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
 }
 
@@ -395,6 +400,20 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     if (lane == 0) qi = atomicAdd(p.next_query, 1u);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= (unsigned)p.nq) break;
+    if (p.ready) {
+      // wait (bounded) until the piece holding this query has been copied in
+      const unsigned need = qi / p.ready_step + 1u;
+      int ok = 1;
+      if (lane == 0) {
+        unsigned spins = 0;
+        while (*reinterpret_cast<const volatile unsigned int*>(p.ready) < need) {
+          __nanosleep(200);
+          if (++spins > (1u << 23)) { ok = 0; atomicAdd(p.events + 2, 1ull); break; }
+        }
+        __threadfence();
+      }
+      if (!__shfl_sync(FULL, ok, 0)) break;
+    }
 
     // target -> registers (or shared for the generic path)
     if (HB_SEARCH_QREG) load_target<CPL>(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.q, w.qs, lane);

@@ -9,7 +9,7 @@ X = H.sift_like(n, 128, seed=1234); Q = np.ascontiguousarray(H.sift_like(10000, 
 h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=16, num_nodes_search_construction=200, levels=draw_levels(n, 16, 7))
 out = (np.empty((10000, 10), np.int32), np.empty((10000, 10), np.float32))
 for b in (Q,) + out: capi.host_register(b)
-for C in (1, 2, 3, 4, 1):
+for C in (1, 2, 4, 8, 1, 4):
     h.set_param("host_chunks", C)
     for _ in range(3): Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=41, out=out)
     t = time.perf_counter()
