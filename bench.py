@@ -207,7 +207,7 @@ def run_reference(a):
         "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": rec, "index_rows": n},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "build_seconds": build_s, "gpu_launches": 0}), flush=True)
+        "build_seconds": build_s, "gpu_launches": 0}), file=_REAL_STDOUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -409,12 +409,22 @@ def run_ours(a):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1: point fd 1 at stderr for the whole run
+    and keep the real stdout for the one JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _only_json_on_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
