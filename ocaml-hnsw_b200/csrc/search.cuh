@@ -5,11 +5,14 @@
 // The sequential best-first semantics are kept exactly (PARITY): one expansion per iteration,
 // neighbours taken in list order, exact visited set, heaps ordered by (distance, id).  What is
 // parallel is everything inside one expansion: the adjacency row is one coalesced load, the
-// visited test-and-set runs one neighbour per lane, and the distances of all unvisited
-// neighbours are evaluated eight at a time (a team of 8 lanes per vector, 128-bit loads).
+// visited test-and-set runs one neighbour per lane, the distances of all unvisited neighbours
+// are evaluated in one batch, eight vectors per round (a team of 8 lanes per vector, 128-bit
+// loads, packed FFMA2), and the candidates are accepted and merged into the beam 32 at a time
+// with the decisions the one-by-one loop would have taken.
 //
 // Per-warp shared memory: the beam (`near`, <= ef sorted keys), a tie list, the compacted
-// neighbour ids/distances of the current expansion, the query, the visited hash.
+// neighbour ids/distances of the current expansion, the query, the visited hash (or, for large
+// beams, one n-bit set per warp in global memory).
 #pragma once
 #include "common.cuh"
 
