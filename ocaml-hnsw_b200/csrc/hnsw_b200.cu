@@ -194,14 +194,15 @@ int search_resident(int cpl, int threads, size_t smem) {
 // Visited set of a query: exact open-addressing hash in shared memory, or one n-bit set per warp
 // in global memory.  The hash costs shared memory (fewer resident warps: throughput is linear in
 // resident warps up to ~24 per SM); the bitset costs one global atomic round trip per expansion
-// and an n/8-byte clear per query.  Bitset when the hash would leave fewer than 24 warps per SM
+// and an n/8-byte clear per query.  Bitset when the hash would leave fewer than 16 warps per SM
+// (measured cross-over on the 1M x 128 shape: ef ~ 72)
 // and the clear is small next to the vectors the query reads (~26 * ef of them).
 bool use_bitset_visited(const hnswb200_index* x, int ef, int smem_per_warp_hash, int64_t n_nodes) {
   if (x->param_visited_mode == 1) return false;
   if (x->param_visited_mode == 2) return true;
   if (x->param_hash_slots > 0) return false;
   const double clear_bytes = (double)n_nodes / 8.0, query_bytes = 26.0 * ef * 4.0 * x->dim;
-  return smem_per_warp_hash > (227 * 1024) / (4 * HB_SEARCH_MINB) - 256 && clear_bytes <= 0.3 * query_bytes;
+  return smem_per_warp_hash > (227 * 1024) / 16 - 256 && clear_bytes <= 0.3 * query_bytes;
 }
 
 SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {

@@ -14,7 +14,7 @@ print(f"build {time.time()-t:.2f}s lib {st.build_seconds:.2f}s ndist/ins {st.bui
 gt, _ = H.brute_force_knn_l2(X, Q, 10, return_ids=True)
 for mode in (0,):
     h.set_param("visited_mode", mode)
-    for ef in (16, 32, 41, 48, 64, 128):
+    for ef in (41, 56, 64, 72, 80, 128):
         ms = []
         for _ in range(3):
             ids, _ = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=ef); s = h.stats(); ms.append(s.search_kernel_ms)
