@@ -291,6 +291,9 @@ struct Hnsw {
   Counters counters;                 // charged by insert(); queries charge the Counters they are given
   std::vector<int32_t> levels;       // the level drawn for each insert (bookkeeping for export)
   uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+  // Hnsw.Ba's Nearest.insert_distance (lib/hnsw.ml:494-506) accepts a candidate whose distance EQUALS
+  // the current maximum; path B (ohnsw.ml:574) does not.  Off = path B, the default.
+  bool accept_ties = false;
 
   Hnsw() { layers.emplace_back(); }
 
@@ -364,7 +367,8 @@ struct Hnsw {
         if (!visited.mem(e)) {
           visited.add(e);
           HeapElt he = element(target, e, c);                            // :573
-          if ((int)nearest_maxq.size() < k || he.distance < nearest_maxq.top().distance) {  // :574
+          if ((int)nearest_maxq.size() < k ||
+              (accept_ties ? he.distance <= nearest_maxq.top().distance : he.distance < nearest_maxq.top().distance)) {  // :574 / hnsw.ml:494-506
             visit_me.push(he);
             nearest_maxq.push(he);
             if ((int)nearest_maxq.size() > k) nearest_maxq.pop();       // :577

@@ -57,6 +57,8 @@ void* orc_vec_create(int dim, int metric, int order) {
   return v;
 }
 void orc_vec_destroy(void* p) { delete (VecHandle*)p; }
+// 1: the Hnsw.Ba acceptance rule (ties with the current maximum are accepted, lib/hnsw.ml:494-506)
+void orc_vec_set_accept_ties(void* p, int on) { ((VecHandle*)p)->h.accept_ties = on != 0; }
 
 // build_batch_bigarray (ohnsw.ml:840-857): n sequential inserts in row order.  May be called
 // again to keep inserting (the reference's `insert`, :766).  levels may be null.

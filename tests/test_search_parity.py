@@ -257,3 +257,32 @@ def test_device_queries_with_padded_rows():
         assert np.array_equal(ids.cpu().numpy(), ids_h) and np.array_equal(d.cpu().numpy().view(np.uint32), d_h.view(np.uint32))
     with pytest.raises(ValueError, match="row_floats"):
         h.set_param("row_floats", 64)                      # not on a built index
+
+
+def test_hnsw_ba_acceptance_rule_on_tie_heavy_data():
+    """HNSW_BA flavour: candidates that TIE with the beam's maximum are accepted (lib/hnsw.ml:494-506).
+    Integer data makes ties the common case; ids, distances and counters must equal the oracle run
+    with the same rule, and differ from the path-B rule somewhere (the rule is really exercised)."""
+    rng = np.random.default_rng(12)
+    X = np.unique(rng.integers(0, 4, (4000, 12)).astype(np.float32), axis=0)
+    X = X[rng.permutation(len(X))]
+    Q = rng.integers(0, 4, (300, 12)).astype(np.float32)
+    o = _oracle_index(X, 8, 40)
+    h = Ohnsw.Hgraph(12, capi.L2, 8, 40, flavour=capi.FLAVOUR_HNSW_BA).import_graph(X, o.export())
+    ids_b, d_b = o.search(Q, 10, 30)
+    o.set_accept_ties(True)
+    differs = False
+    for k, ef in [(10, 10), (10, 30), (5, 64)]:
+        ids_o, d_o, cnt_o = o.search(Q, k, ef, counters=True)
+        ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=k, ef=ef)
+        d_o = np.where(ids_o < 0, np.float32(np.inf), d_o)               # Hnsw.Ba pads with +inf (lib/hnsw.ml:770)
+        assert_same_results(ids_g, d_g, ids_o, d_o)
+        cnt_g = h.last_search_counters(len(Q)).astype(np.uint64)
+        bad = np.nonzero((cnt_g != cnt_o).any(axis=1))[0]
+        # a query with more than 32 evicted candidates tied at the top leaves the surplus unexpanded
+        # (counted in search_tie_overflows): same rows here, less work — only those may differ
+        assert bad.size <= h.stats().search_tie_overflows, (
+            f"k={k} ef={ef}: counters differ for {bad.size} queries, tie overflows {h.stats().search_tie_overflows}")
+        if (k, ef) == (10, 30):
+            differs = not np.array_equal(ids_o, ids_b)
+    assert differs, "the two acceptance rules gave identical results: the test data has no ties at the boundary"
