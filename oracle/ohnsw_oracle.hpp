@@ -294,6 +294,11 @@ struct Hnsw {
   // Hnsw.Ba's Nearest.insert_distance (lib/hnsw.ml:494-506) accepts a candidate whose distance EQUALS
   // the current maximum; path B (ohnsw.ml:574) does not.  Off = path B, the default.
   bool accept_ties = false;
+  // The other Hnsw.Ba build parameters the GPU's HNSW_BA flavour follows (lib/hnsw.ml:753-758,
+  // hnsw_algo.ml:596-599, 661-667): M links for a new node on layer 0 too, and a candidate set no
+  // larger than that is kept whole.  Pruning stays path B's (w.r.t. the pruned node): path A's
+  // prune-by-distance-to-the-inserted-point (Q6) and do_not_isolate are not restated.
+  bool ba_build = false;
 
   Hnsw() { layers.emplace_back(); }
 
@@ -382,8 +387,12 @@ struct Hnsw {
   }
 
   // select_neighbours (:647-663).  Consumes the candidate min-queue.
-  Neighbours select_neighbours(MinHeap& possible, int num_neighbours, Counters& c) const {
+  Neighbours select_neighbours(MinHeap& possible, int num_neighbours, Counters& c, bool keep_all = false) const {
     Neighbours selected;
+    if (keep_all && (int)possible.size() <= num_neighbours) {            // hnsw_algo.ml:596-599
+      while (!possible.empty()) { selected.add(possible.top().node); possible.pop(); }
+      return selected;
+    }
     while (!possible.empty()) {
       HeapElt e = possible.top(); possible.pop();
       bool all = true;                                                  // Neighbours.for_all, head first
@@ -435,8 +444,9 @@ struct Hnsw {
       MinHeap nearest = search_k(layer, visited, w_queue, num_nodes_search_construction, target, counters);  // :811
       w_queue = nearest;                                                // :814-816 swap
       int nc = layer == 0 ? 2 * num_connections : num_connections;      // :818
+      int n_new = ba_build ? num_connections : nc;                      // lib/hnsw.ml:753-758
       MinHeap copy = w_queue;                                           // MinQueue.copy (:819)
-      Neighbours neighbours = select_neighbours(copy, nc, counters);
+      Neighbours neighbours = select_neighbours(copy, n_new, counters, ba_build);
       graph.set_connections_for_new_node(new_node, neighbours);         // :820
       const std::vector<int32_t> iter_list = neighbours.list;           // List.iter holds the old immutable list
       for (int32_t neighbour : iter_list) {                             // :821-829

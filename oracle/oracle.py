@@ -40,6 +40,7 @@ def lib():
             "orc_vec_create": (vp, [i32, i32, i32]),
             "orc_vec_destroy": (None, [vp]),
             "orc_vec_set_accept_ties": (None, [vp, i32]),
+            "orc_vec_set_ba_build": (None, [vp, i32]),
             "orc_vec_build": (i32, [vp, vp, i64, i32, i32, vp]),
             "orc_vec_search": (i32, [vp, vp, i64, i32, i32, vp, vp, vp]),
             "orc_vec_search_mt": (i32, [vp, vp, i64, i32, i32, vp, vp, i32, P(f64), vp]),
@@ -147,6 +148,11 @@ class VecOracle:
     def set_accept_ties(self, on=True):
         """Hnsw.Ba's acceptance rule (lib/hnsw.ml:494-506): candidates that tie with the current maximum enter."""
         lib().orc_vec_set_accept_ties(self._h, 1 if on else 0)
+        return self
+
+    def set_ba_build(self, on=True):
+        """Hnsw.Ba's build parameters as the GPU's HNSW_BA flavour follows them (see ohnsw_oracle.hpp)."""
+        lib().orc_vec_set_ba_build(self._h, 1 if on else 0)
         return self
 
     # Ohnsw.build_batch_bigarray (ohnsw.ml:840) / repeated Ohnsw.insert (:766)

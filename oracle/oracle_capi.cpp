@@ -59,6 +59,8 @@ void* orc_vec_create(int dim, int metric, int order) {
 void orc_vec_destroy(void* p) { delete (VecHandle*)p; }
 // 1: the Hnsw.Ba acceptance rule (ties with the current maximum are accepted, lib/hnsw.ml:494-506)
 void orc_vec_set_accept_ties(void* p, int on) { ((VecHandle*)p)->h.accept_ties = on != 0; }
+// 1: the Hnsw.Ba build parameters (M links for a new node on every layer, small candidate sets kept whole)
+void orc_vec_set_ba_build(void* p, int on) { ((VecHandle*)p)->h.ba_build = on != 0; }
 
 // build_batch_bigarray (ohnsw.ml:840-857): n sequential inserts in row order.  May be called
 // again to keep inserting (the reference's `insert`, :766).  levels may be null.

@@ -131,6 +131,24 @@ def test_sequential_gpu_build_is_the_oracle_graph(kind, n, dim, M, efC):
     assert h.stats().build_n_dist >= o.counters()[0] * 0.9
 
 
+def test_sequential_hnsw_ba_flavour_build_is_the_oracle_graph():
+    """HNSW_BA flavour, build_batch = 1: ties accepted in the insert search, M links for a new node on
+    layer 0 too, small candidate sets kept whole — against the oracle with the same three rules."""
+    n, dim, M, efC = 1200, 24, 6, 30
+    X = np.unique(np.random.default_rng(60).integers(0, 6, (n, dim)).astype(np.float32), axis=0)
+    X = X[np.random.default_rng(61).permutation(len(X))]
+    n = len(X)
+    lv = draw_levels(n, M)
+    lv[0] = 0
+    o = O.VecOracle(dim).set_accept_ties(True).set_ba_build(True).build(X, M, efC, lv)
+    h = Ohnsw.Hgraph(dim, Ohnsw.distance_l2, M, efC, flavour=capi.FLAVOUR_HNSW_BA)
+    h.set_param("build_batch", 1)
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), n, capi.ptr(lv)))
+    g = h.export_graph()
+    _same_graph(g, o.export())
+    assert g.degree(0).max() <= 2 * M
+
+
 def test_committed_fixture_build_and_search(golden_dir):
     """tests/golden/oracle_small.npz: the sequential GPU build reproduces the frozen graph, and the GPU
     search on it the frozen rows and work counters."""
