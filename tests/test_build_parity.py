@@ -131,6 +131,23 @@ def test_sequential_gpu_build_is_the_oracle_graph(kind, n, dim, M, efC):
     assert h.stats().build_n_dist >= o.counters()[0] * 0.9
 
 
+def test_sequential_build_then_inserts_is_the_oracle_graph():
+    """Ohnsw.build_batch_bigarray on a prefix, then Ohnsw.insert one vector at a time and in a block
+    (lib/ohnsw.ml:766-837), all in sequential mode: still the graph the oracle builds in one go."""
+    n, dim, M, efC = 900, 32, 8, 40
+    X = uniform(n, dim, 71)
+    lv = draw_levels(n, M)
+    lv[0] = 0
+    o = O.VecOracle(dim).build(X, M, efC, lv)
+    h = Ohnsw.Hgraph(dim, Ohnsw.distance_l2, M, efC)
+    h.set_param("build_batch", 1)
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X[:500]), 500, capi.ptr(lv[:500])))
+    for i in range(500, 520):
+        Ohnsw.insert(h, X[i], num_connections=M, num_nodes_search_construction=efC, levels=lv[i:i + 1])
+    Ohnsw.insert(h, X[520:], levels=lv[520:])
+    _same_graph(h.export_graph(), o.export())
+
+
 def test_sequential_hnsw_ba_flavour_build_is_the_oracle_graph():
     """HNSW_BA flavour, build_batch = 1: ties accepted in the insert search, M links for a new node on
     layer 0 too, small candidate sets kept whole — against the oracle with the same three rules."""
