@@ -95,7 +95,7 @@ struct hnswb200_index {
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // host-buffer search: copy / compute overlap
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t param_host_chunks = 0, param_strict_ties = 0;
-  unsigned int h_ready[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned int* h_ready = nullptr;      // pinned: the "pieces ready" values the copy stream writes after each piece
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
   DevBuf<int32_t> d_ids;
@@ -384,6 +384,8 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   if (C > 1 && !x->aux_stream[0]) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&x->aux_stream[0], cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&x->aux_event[0], cudaEventDisableTiming));
+    CUDA_CHECK(cudaMallocHost(&x->h_ready, 8 * sizeof(unsigned int)));
+    for (int c = 0; c < 8; c++) x->h_ready[c] = (unsigned)(c + 1);
   }
   // d_next[0] = work counter, d_next[1] = pieces of the batch copied so far
   CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, 8 * sizeof(unsigned int), s0));
@@ -408,7 +410,6 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
       const int64_t q0 = (int64_t)step * c, m = std::min<int64_t>(step, nq - q0);
       if (m <= 0) break;
       upload_rows(x->d_q.p + (size_t)q0 * x->ld, x->ld, queries + (size_t)q0 * x->dim, x->dim, m, sc);
-      x->h_ready[c] = (unsigned)(c + 1);
       CUDA_CHECK(cudaMemcpyAsync(x->d_next.p + 1, &x->h_ready[c], sizeof(unsigned int), cudaMemcpyHostToDevice, sc));
     }
   }
@@ -582,6 +583,7 @@ int hnswb200_destroy(hnswb200_index* x) {
     if (x->stream) cudaStreamSynchronize(x->stream);
     if (x->ev0) cudaEventDestroy(x->ev0);
     if (x->ev1) cudaEventDestroy(x->ev1);
+    if (x->h_ready) cudaFreeHost(x->h_ready);
     for (cudaStream_t a : x->aux_stream) if (a) cudaStreamDestroy(a);
     for (cudaEvent_t e : x->aux_event) if (e) cudaEventDestroy(e);
     if (x->stream) cudaStreamDestroy(x->stream);
