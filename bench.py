@@ -138,6 +138,16 @@ def profiled_traffic(workload, ef):
         return None
 
 
+def host_threads(O):
+    """All the host threads the CPU arm can use: torchrun exports OMP_NUM_THREADS=1, which is not a
+    property of the machine — take the affinity mask instead."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    return max(int(O.lib().orc_num_threads()), avail)
+
+
 def measured_peak():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -159,7 +169,7 @@ def run_reference(a):
         return
     import ocaml_hnsw_b200.dataset as D           # numpy generators only; no GPU call on this arm
     from oracle import oracle as O
-    threads = O.lib().orc_num_threads()
+    threads = host_threads(O)
     n = min(a.ref_n, a.n)
     X = np.ascontiguousarray(make_data(a, a.n, 1234)[:n])                 # a true prefix of the GPU arm's dataset
     Q = make_data(a, a.nq, 4321)
@@ -169,9 +179,9 @@ def run_reference(a):
     o = O.VecOracle(a.dim, om).build(X, a.M, a.efc, lv)
     build_s = time.time() - t0
     gt_n = min(a.nq, 2000)
-    gt, _ = O.bruteforce(X, Q[:gt_n], a.k, om)
+    gt, _ = O.bruteforce(X, Q[:gt_n], a.k, om, nthreads=threads)
     def recall_at(ef):
-        ids = o.search_mt(Q[:gt_n], a.k, ef)[0]
+        ids = o.search_mt(Q[:gt_n], a.k, ef, nthreads=threads)[0]
         return float(np.mean([len(set(g.tolist()) & set(i[i >= 0].tolist())) / a.k for g, i in zip(gt, ids)]))
 
     ef_star, rec, prev = EF_SWEEP[-1], 0.0, None
@@ -193,10 +203,10 @@ def run_reference(a):
             else:
                 lo_ef = mid
     for _ in range(a.warmup):
-        o.search_mt(Q, a.k, ef_star)
+        o.search_mt(Q, a.k, ef_star, nthreads=threads)
     secs = 0.0
     for _ in range(a.steps):
-        secs += o.search_mt(Q, a.k, ef_star)[2]
+        secs += o.search_mt(Q, a.k, ef_star, nthreads=threads)[2]
     qps = a.nq * a.steps / secs
     sample = (f"index built by the CPU port over the first {n} of {a.n} rows (sequential build {build_s:.1f} s), "
               f"{a.nq} queries/step, ef={ef_star}, recall@{a.k}={rec:.4f} on {gt_n} queries")
@@ -372,11 +382,11 @@ def run_ours(a):
         g = h.export_graph()
         o = O.VecOracle(a.dim, O.METRIC_L2 if a.metric == "l2" else O.METRIC_ANGULAR)
         o.import_graph(X, O.Graph(g.n, g.max_layer, g.entry, g.offsets, g.nbrs, g.levels))
-        threads = O.lib().orc_num_threads()
-        o.search_mt(Q[:1000], a.k, ef_star)
+        threads = host_threads(O)
+        o.search_mt(Q[:1000], a.k, ef_star, nthreads=threads)
         reps, secs, ids_o = 0, 0.0, None
         while secs < 10.0 and reps < 50:
-            ids_o, _, s, _ = o.search_mt(Q, a.k, ef_star)
+            ids_o, _, s, _ = o.search_mt(Q, a.k, ef_star, nthreads=threads)
             secs += s; reps += 1
         one = o.search_mt(Q[:2000], a.k, ef_star, nthreads=1)[2]
         same = bool(np.array_equal(ids_o, out[0]))
