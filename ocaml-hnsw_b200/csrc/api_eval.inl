@@ -50,6 +50,7 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   DevBuf<__nv_bfloat16> x_hi, x_lo, q_hi, q_lo;
   DevBuf<float> x_norm, scal, bound;
   DevBuf<int> flags;
+  DevBuf<unsigned int> gthr;
   DevBuf<uint64_t> partial;
   x_hi.reserve((size_t)n * kp); x_lo.reserve((size_t)n * kp); q_hi.reserve((size_t)nq * kp); q_lo.reserve((size_t)nq * kp);
   x_norm.reserve((size_t)n); scal.reserve(4); flags.reserve((size_t)nq + 4);
@@ -71,11 +72,13 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   int splits = std::max(1, std::min(32, (8 * num_sms + qblocks - 1) / qblocks));       // >= ~8 waves of CTAs
   int64_t split_len = ((n + splits - 1) / splits + hb::TC_N - 1) / hb::TC_N * hb::TC_N;
   splits = (int)((n + split_len - 1) / split_len);
+  gthr.reserve((size_t)nq);
+  CUDA_CHECK(cudaMemsetAsync(gthr.p, 0xff, (size_t)nq * sizeof(unsigned int), s));     // ordered-float +NaN/inf side: no threshold yet
   partial.reserve((size_t)splits * hb::TC_HALVES * nq * hb::TC_KP);
   bound.reserve((size_t)splits * hb::TC_HALVES * nq);
   hb::TcParams p{};
   p.x_hi = x_hi.p; p.x_lo = x_lo.p; p.q_hi = q_hi.p; p.q_lo = q_lo.p; p.x_norm = x_norm.p;
-  p.n = n; p.nq = nq; p.kp = kp; p.segs = any_lo ? 3 : 1; p.split_len = split_len; p.partial = partial.p; p.bound = bound.p;
+  p.n = n; p.nq = nq; p.kp = kp; p.segs = any_lo ? 3 : 1; p.split_len = split_len; p.partial = partial.p; p.bound = bound.p; p.gthr = gthr.p;
   size_t smem = hb::tc_smem_bytes();
   CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tm.lap("(sync, alloc)");

@@ -53,6 +53,7 @@ struct TcParams {
   int64_t split_len;           // data rows per gridDim.y slice (multiple of TC_N)
   uint64_t* partial;           // [gridDim.y * TC_HALVES][nq][TC_KP] keys (approximate distance, id)
   float* bound;                // [gridDim.y * TC_HALVES][nq] approximate distance below which nothing was rejected
+  unsigned int* gthr;          // [nq] ordered-float: the tightest threshold any CTA has reached for the query (shared by all splits)
 };
 
 __host__ __device__ inline size_t tc_smem_bytes() {
@@ -159,17 +160,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
   float thr = __int_as_float(0x7f800000);
 
   const int64_t ntiles = (x_end - x_begin + TC_N - 1) / TC_N;
-  const int64_t total = ntiles * nchunks;       // k-chunks this CTA streams, tile after tile
+  const uint32_t total = (uint32_t)(ntiles * nchunks);       // k-chunks this CTA streams, tile after tile
 
   // stage a k-chunk: chunk index g -> (tile, segment, kc)
-  auto issue = [&](int64_t gch) {
+  // (32-bit index arithmetic: a split holds < 2^31 / TC_N tiles of at most a few dozen chunks)
+  auto issue = [&](uint32_t gch) {
     const int s = (int)(gch % TC_STAGES);
-    const int64_t tile = gch / nchunks;
-    const int c = (int)(gch % nchunks), seg = c / kchunks, kc = c % kchunks;
+    const uint32_t tile = gch / (uint32_t)nchunks;
+    const int c = (int)(gch - tile * (uint32_t)nchunks), seg = c / kchunks, kc = c - seg * kchunks;
     const __nv_bfloat16* A = seg == 1 ? p.q_lo : p.q_hi;
     const __nv_bfloat16* B = seg == 2 ? p.x_lo : p.x_hi;
     const uint32_t sA = smem_u32(stages + (size_t)s * TC_STAGE_BYTES), sB = sA + TC_A_BYTES;
-    const int64_t xb = x_begin + tile * TC_N;
+    const int64_t xb = x_begin + (int64_t)tile * TC_N;
 #pragma unroll
     for (int i = 0; i < TC_M * 8 / TC_THREADS; i++) {
       const int idx = tid + TC_THREADS * i, row = idx >> 3, ch = idx & 7;
@@ -185,14 +187,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  for (int64_t g = 0; g < TC_STAGES - 1; g++) {
+  for (uint32_t g = 0; g < TC_STAGES - 1; g++) {
     if (g < total) issue(g); else asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
-  for (int64_t g = 0; g < total; g++) {
-    const int s = (int)(g % TC_STAGES);
-    const int c = (int)(g % nchunks);
-    const int64_t tile = g / nchunks;
+  int s = 0, c = 0;                                // stage and chunk-in-tile of chunk g, kept incrementally
+  uint32_t tile = 0;
+  for (uint32_t g = 0; g < total; g++, s = s + 1 == TC_STAGES ? 0 : s + 1) {
     // this thread's part of chunk g has landed; publish to the async proxy; everyone's part has landed
     asm volatile("cp.async.wait_group %0;" ::"n"(TC_STAGES - 2) : "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -210,9 +211,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
       if (c == nchunks - 1) umma_commit(smem_u32(bars + TC_STAGES));   // the tile's accumulator is complete
     }
     // refill: chunk g + STAGES - 1 goes into the stage chunk g - 1 used
-    const int64_t nx = g + TC_STAGES - 1;
+    const uint32_t nx = g + TC_STAGES - 1;
     if (nx < total) {
-      if (g >= 1) mbar_wait(smem_u32(bars + (int)((g - 1) % TC_STAGES)), (uint32_t)(((g - 1) / TC_STAGES) & 1));
+      if (g >= 1) mbar_wait(smem_u32(bars + (s == 0 ? TC_STAGES - 1 : s - 1)), ((g - 1) / TC_STAGES) & 1u);
       issue(nx);
     } else {
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -220,8 +221,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
 
     if (c == nchunks - 1) {
       // ---- epilogue of this tile: one accumulator row (query) per thread
-      const int64_t xb = x_begin + tile * TC_N;
+      const int64_t xb = x_begin + (int64_t)tile * TC_N;
       for (int i = tid; i < TC_N; i += TC_THREADS) xn[i] = xb + i < x_end ? p.x_norm[xb + i] : __int_as_float(0x7f800000);
+      // every split of a query tightens one shared threshold: a value rejected under it can never
+      // be among the query's TC_KP best, whichever split it lives in (the bound stays valid because
+      // thresholds only decrease)
+      if (q0 + row < p.nq) thr = fminf(thr, ord2f(__ldcg(p.gthr + q0 + row)));
       mbar_wait(smem_u32(bars + TC_STAGES), (uint32_t)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __syncthreads();
@@ -239,7 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
           if (cnt < TC_KP) cnt++;
         }
         ns = 0;
-        if (cnt == TC_KP) thr = key_dist(my_list[TC_KP - 1]);
+        if (cnt == TC_KP) {
+          const float t16 = key_dist(my_list[TC_KP - 1]);
+          if (t16 < thr) { thr = t16; if (q0 + row < p.nq) atomicMin(p.gthr + q0 + row, f2ord(t16)); }
+        }
       };
 #pragma unroll 1
       for (int cb = half * (TC_N / 32 / TC_HALVES); cb < (half + 1) * (TC_N / 32 / TC_HALVES); cb++) {
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) bruteforce_tc_kernel(const TcPa
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
     }
+    if (++c == nchunks) { c = 0; tile++; }
   }
 
   // partial lists and the rejection bound of this split
