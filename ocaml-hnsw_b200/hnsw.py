@@ -25,11 +25,12 @@ class Ba:
 
     @staticmethod
     def knn(hgraph, point, *, num_neighbours_search=5, num_neighbours):
-        """Hnsw.Ba.knn (lib/hnsw.ml:763-767) -> [(node, distance_to_target)], nearest first."""
+        """Hnsw.Ba.knn (lib/hnsw.ml:763-767) -> [(node, distance_to_target)], nearest first.  Nodes are numbered
+        from 1 as in Hnsw.Ba (lib/hnsw.ml:313-325: node k is `Mat.col m k`), i.e. row index + 1."""
         t = np.asarray(point, np.float32)[None, :]
         ef = max(num_neighbours_search, num_neighbours)
         ids, d = ohnsw.knn_batch_bigarray(hgraph, t, k=num_neighbours, ef=ef)
-        return [(int(i), float(x)) for i, x in zip(ids[0], d[0]) if i >= 0]
+        return [(int(i) + 1, float(x)) for i, x in zip(ids[0], d[0]) if i >= 0]
 
     @staticmethod
     def knn_batch(hgraph, batch, *, num_neighbours_search, num_neighbours):

@@ -79,15 +79,21 @@ module Ba = struct
     set_flavour h 1;
     build_ h data no_levels;
     h
-  let knn_batch (h : t) (batch : Lacaml.S.mat) ~num_neighbours_search ~num_neighbours : Lacaml.S.mat =
+  let search (h : t) (batch : Lacaml.S.mat) ~num_neighbours_search ~num_neighbours =
     let nq = Lacaml.S.Mat.dim2 batch in
     let distances = Lacaml.S.Mat.create num_neighbours nq in
     let ids32 = Bigarray.Array2.create Bigarray.int32 Bigarray.c_layout nq num_neighbours in
     search_ h batch num_neighbours (max num_neighbours_search num_neighbours) ids32 distances;
-    distances                                                              (* +inf padded, lib/hnsw.ml:770 *)
+    ids32, distances
+  (* lib/hnsw.ml:769-777: distances only, +inf padded (:770) *)
+  let knn_batch (h : t) (batch : Lacaml.S.mat) ~num_neighbours_search ~num_neighbours : Lacaml.S.mat =
+    snd (search h batch ~num_neighbours_search ~num_neighbours)
+  (* lib/hnsw.ml:763-767: (node, distance) pairs, nearest first; Hnsw.Ba numbers nodes from 1 (:313-325).
+     A maintainer maps the pair onto Hnsw_algo.value_distance (lib/hnsw_algo.ml:85). *)
   let knn (h : t) (point : value) ~num_neighbours_search ~num_neighbours =
-    let d = knn_batch h (Lacaml.S.Mat.of_col_vecs [| point |]) ~num_neighbours_search ~num_neighbours in
-    List.init num_neighbours (fun i -> d.{i + 1, 1})
+    let ids, d = search h (Lacaml.S.Mat.of_col_vecs [| point |]) ~num_neighbours_search ~num_neighbours in
+    List.filter (fun (i, _) -> i >= 1)
+      (List.init num_neighbours (fun i -> Int32.to_int ids.{0, i} + 1, d.{i + 1, 1}))
 end
 
 (* benchmark/dataset.ml:15-30 *)

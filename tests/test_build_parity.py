@@ -282,6 +282,10 @@ def test_hnsw_ba_flavour_build():
     few = Hnsw.Ba.build(X[:4], num_neighbours=4, num_neighbours_build=10, levels=np.zeros(4, np.int32))
     d = Hnsw.Ba.knn_batch(few, Q[:3], num_neighbours_search=8, num_neighbours=8)
     assert np.isinf(d[:, 4:]).all() and np.isfinite(d[:, :4]).all()          # lib/hnsw.ml:770-771
+    # Hnsw.Ba.knn (lib/hnsw.ml:763-767): (node, distance) pairs, nodes numbered from 1 (:313-325)
+    one = Hnsw.Ba.knn(few, X[2], num_neighbours_search=8, num_neighbours=8)
+    assert len(one) == 4 and one[0] == (3, 0.0) and sorted(n for n, _ in one) == [1, 2, 3, 4]
+    assert [x for _, x in one] == sorted(x for _, x in one)
 
 
 def test_build_argument_errors():
