@@ -13,8 +13,14 @@ reported beside the QPS).  `value` times the search with queries resident in HBM
 public host-buffer call (pinned H2D of the queries + search + D2H of ids and distances).
 
 N > 1 (torchrun, one rank per GPU): the dataset is row-sharded (1M/N rows per GPU), every rank
-searches its shard, one NCCL all-gather + merge kernel per step; `value` = nq / max-over-ranks
-time (total work fixed -> "strong").
+searches its shard and stores its result rows straight into every peer's buffer (symmetric memory;
+one packed NCCL all-gather where that is unavailable), then a barrier and the merge kernel; `value` =
+nq / max-over-ranks time (total work fixed -> "strong").
+
+L2: steps run back to back when one shard's index is more than twice the L2 size (640 MB at N = 1);
+a smaller shard (N = 4, 8, or a small --rows) would be re-read from L2, so every step is then
+preceded by a write of 2 x L2 bytes and timed on its own (`config.l2` says which).  Clocks and
+throttle reasons are sampled by nvidia-smi every 25 ms while the timed loops run (`clocks`).
 
 Synthetic data: the "SIFT-like" generator of SURVEY.md section 8d(b) (16-d latent, fixed random
 projection to 128-d, noise, integer-valued in [0, 218]); iid-uniform data cannot reach 0.95 at any
