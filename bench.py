@@ -59,13 +59,35 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--metric", default="l2", choices=["l2", "angular"],
                     help="angular = SURVEY.md config C3 (GloVe shape): unit-norm Gaussian-mixture vectors, distance 1 - a.b")
-    return ap.parse_args()
+    ap.add_argument("--latent", type=int, default=16, help="latent dimension of the SIFT-like generator")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="a BASELINE.json configuration by name (SURVEY.md section 8d); sets rows/dim/nq/M/metric/latent")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE",
+                    help="hnswb200_set_param on the index before the build (e.g. row_floats=128, stage_rows=8)")
+    a = ap.parse_args()
+    if a.config:
+        for name, v in CONFIGS[a.config].items():
+            setattr(a, name, v)
+    a.params = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in a.set}
+    return a
+
+
+# BASELINE.json `configs`: c2 is the bench line (the default); the others are
+# reproducible one-line runs, `python bench.py --config c4`, `torchrun ... bench.py --gpus 8 --config c5`.
+CONFIGS = {
+    "c1": dict(n=10_000, dim=128, nq=10_000, M=16, efc=100, metric="l2", latent=16),
+    "c2": dict(n=1_000_000, dim=128, nq=10_000, M=16, efc=200, metric="l2", latent=16),
+    "c3": dict(n=1_183_514, dim=100, nq=10_000, M=24, efc=200, metric="angular"),
+    "c4": dict(n=1_000_000, dim=960, nq=1_000, M=16, efc=200, metric="l2", latent=32),
+    "c5": dict(n=10_000_000, dim=96, nq=10_000, M=16, efc=200, metric="l2", latent=16),
+}
 
 
 def workload_name(a):
     if a.metric == "angular":
         return f"unit-norm gaussian-mixture {a.n}x{a.dim} fp32 angular, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
-    return f"sift-like {a.n}x{a.dim} fp32 L2, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
+    lat = "" if a.latent == 16 else f" ({a.latent}-d latent)"
+    return f"sift-like{lat} {a.n}x{a.dim} fp32 L2, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
 
 
 def make_data(a, n, seed):
@@ -73,7 +95,7 @@ def make_data(a, n, seed):
     mixture (256 centres, sigma 0.35) for the angular config."""
     import ocaml_hnsw_b200.dataset as D
     if a.metric == "l2":
-        return D.sift_like(n, a.dim, seed=seed)
+        return D.sift_like(n, a.dim, latent=a.latent, seed=seed)
     centres = np.random.default_rng(99).standard_normal((256, a.dim)).astype(np.float32)
     rng = np.random.default_rng(seed)
     out = np.empty((n, a.dim), np.float32)
@@ -305,7 +327,7 @@ def run_ours(a):
     barrier()
     t0 = time.perf_counter()
     sh = ShardedHgraph.build(metric, X, a.n, num_connections=a.M, num_nodes_search_construction=a.efc,
-                             rank=rank, world=world, levels=lv, device=local_rank)
+                             rank=rank, world=world, levels=lv, device=local_rank, params=a.params)
     torch.cuda.synchronize()
     build_s = max_over_ranks(time.perf_counter() - t0)
     h = sh.local

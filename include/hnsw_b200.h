@@ -102,7 +102,12 @@ typedef struct hnswb200_stats {
   double   layer_mean_degree[16];
   int64_t  layer_isolated[16];
   uint64_t build_visited_overflows;  /* inserts whose visited set left shared memory */
-  uint64_t search_tie_overflows;     /* queries with more than 32 evicted candidates tied at the beam's top distance */
+  uint64_t search_tie_overflows;     /* queries whose list of evicted candidates tied at the beam's top distance outgrew
+                                        shared memory (32) AND its global region (32k): the surplus was not revisited, the
+                                        only way a PARITY search can differ from the reference; hnswb200_search fails on it */
+  uint64_t search_tie_spills;        /* queries whose tie list continued in a global region (exact, just slower) */
+  uint64_t build_dropped_incoming;   /* links dropped because one row received more than 96 new nodes in ONE build batch
+                                        (the 96 smallest ids are kept and re-selected); 0 on every shape measured */
 } hnswb200_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -119,9 +124,8 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
  * n / build_ratio nodes, default 64), "host_chunks" (2..8: hnswb200_search streams batches of
  * >= 4096 queries to the GPU in this many pieces behind ONE already running search kernel whose
  * warps wait for the piece that holds their query; default: copy first, then search),
- * "strict_ties" (1: a PARITY
- * search fails when a query had more than 32 evicted candidates tied at the beam's top distance —
- * heavy duplicate vectors — instead of only counting it in hnswb200_stats.search_tie_overflows),
+ * "stage_rows" (rows of >= 1 KB are gathered with cp.async.bulk into a per-warp shared-memory ring of
+ * this many rows, 4..32; 0 = automatic, -1 = per-lane 128-bit loads instead),
  * "row_floats" (stride of a vector row in floats, a multiple of 4 >= dim; default dim rounded up to
  * 4; only on an empty index). */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);

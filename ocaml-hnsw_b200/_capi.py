@@ -32,7 +32,8 @@ class Stats(C.Structure):
                 ("gpu_launches", C.c_uint64), ("num_layers", C.c_int32),
                 ("layer_nodes", C.c_int64 * 16), ("layer_min_degree", C.c_int32 * 16),
                 ("layer_max_degree", C.c_int32 * 16), ("layer_mean_degree", C.c_double * 16),
-                ("layer_isolated", C.c_int64 * 16), ("build_visited_overflows", C.c_uint64), ("search_tie_overflows", C.c_uint64)]
+                ("layer_isolated", C.c_int64 * 16), ("build_visited_overflows", C.c_uint64), ("search_tie_overflows", C.c_uint64),
+                ("search_tie_spills", C.c_uint64), ("build_dropped_incoming", C.c_uint64)]
 
 
 class HnswB200Error(RuntimeError):

@@ -69,7 +69,9 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   pl.cpl = cpl <= 4 ? cpl : 0;
   pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
   pl.ef_cap = round_up(ef, 32);
-  int extra = pl.q_chunks * 16 + bp.sel_cap * 4;
+  pl.stage_slots = stage_slots_for(x, pl.cpl);
+  const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
+  int extra = pl.q_chunks * 16 + bp.sel_cap * 4 + stage_bytes;
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 32 * ef), 128);
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + extra;
@@ -89,7 +91,7 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   pl.smem = (size_t)pl.warps * pl.smem_per_warp;
   pl.grid = x->num_sms * build_search_resident(pl.cpl, pl.warps * 32, pl.smem);
   // phase 2
-  bp.link_smem_per_warp = hb::link_smem_per_warp(bp.ucap, bp.sel_cap, pl.q_chunks);
+  bp.link_smem_per_warp = hb::link_smem_per_warp(bp.ucap, bp.sel_cap, pl.q_chunks) + stage_bytes;
   bp.link_warps = 8;
   while (bp.link_warps > 1 && (size_t)bp.link_warps * bp.link_smem_per_warp > (size_t)x->max_smem_optin) bp.link_warps--;
   if ((size_t)bp.link_smem_per_warp > (size_t)x->max_smem_optin) fail(HNSWB200_EINVAL, "build: dimension / num_connections too large for shared memory");
@@ -154,9 +156,11 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   sp.queries = nullptr; sp.nq = B; sp.ef = x->efC; sp.k = x->efC; sp.ef_cap = pl.ef_cap;
   sp.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA; sp.pad_inf = 0;
   sp.hash_slots = pl.hash_slots; sp.q_smem_chunks = pl.q_chunks; sp.smem_per_warp = pl.smem_per_warp; sp.nb_cap = pl.nb_cap;
+  sp.stage_slots = pl.stage_slots;
   sp.out_ids = nullptr; sp.out_dists = nullptr; sp.counters = nullptr; sp.next_query = nullptr;
   sp.bitset_pool = x->d_bitpool.p; sp.pool_busy = x->d_pool_busy.p; sp.pool_size = x->pool_size; sp.words = x->pool_words;
   sp.events = x->d_events.p;
+  sp.tie_pool = x->d_tie_pool.p; sp.tie_busy = x->d_tie_busy.p; sp.tie_slots = TIE_SLOTS; sp.tie_cap = TIE_CAP;
   p.adj0 = x->adj0.p; p.adjU = x->adjU.p; p.level = x->level.p; p.row_owner = x->row_owner.p;
   p.n0 = (int)n0; p.B = (int)B;
   p.sel0 = bpl.sel0; p.selU = bpl.selU; p.cap0 = bpl.cap0; p.capU = bpl.capU; p.keep_all = bpl.keep_all;
@@ -188,7 +192,8 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
 
   if (x->param_build_batch == 1) {
     // sequential inserts: the reference's own link order, one warp (build.cuh, build_link_seq_kernel)
-    size_t smem = (size_t)hb::link_seq_smem(bpl.ucap, bpl.sel_cap, pl.q_chunks);
+    size_t smem = (size_t)hb::link_seq_smem(bpl.ucap, bpl.sel_cap, pl.q_chunks) +
+                  (pl.stage_slots ? (size_t)hb::stage_smem_bytes(pl.stage_slots, x->ld / 4) : 0);
     switch (pl.cpl) {
 #define HB_SEQ(C)                                                                                                   \
       case C:                                                                                                       \
@@ -261,6 +266,7 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   if (n_new < 0) fail(HNSWB200_EINVAL, "build: n < 0");
   if (n_new == 0) return;
   if (!data) fail(HNSWB200_EINVAL, "build: data is NULL");
+  if (x->poisoned) fail(HNSWB200_ECUDA, "the index is unusable: an earlier build/insert call failed half-way");
   const int64_t n_old = x->n, n_tot = n_old + n_new;
   if (n_tot >= (int64_t(1) << 31) - 1) fail(HNSWB200_EINVAL, "build: too many nodes");
   cudaStream_t s = x->stream;
@@ -268,7 +274,9 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   // levels, upper-row bookkeeping (host mirrors are authoritative)
   std::vector<int8_t> lvl_new((size_t)n_new);
   for (int64_t i = 0; i < n_new; i++) {
-    int l = levels ? levels[i] : draw_level(x);
+    // a level the library drew itself is capped at the 16 layers the index holds (P(level > 15) is ~2e-5 per
+    // node at M = 2 and nil at practical M); a caller-supplied level outside 0..15 is an argument error
+    int l = levels ? levels[i] : std::min(draw_level(x), 15);
     if (n_old + i == 0) l = 0;                       // the first node is the entry of layer 0 (:774-778)
     if (l < 0 || l > 15) fail(HNSWB200_EINVAL, "build: level must be in 0..15");
     lvl_new[(size_t)i] = (int8_t)l;
@@ -328,10 +336,10 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   BuildPlan bpl = plan_build(x, n_tot);
   x->b_ctr.reserve(CTR_N);
   x->b_counters.reserve(4);
-  x->d_events.reserve(2);
+  x->d_events.reserve(4);
   CUDA_CHECK(cudaMemsetAsync(x->b_counters.p, 0, 4 * sizeof(unsigned long long), s));
-  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 2 * sizeof(unsigned long long), s));
-  ensure_pool(x, bpl.sp.grid * bpl.sp.warps, n_tot);
+  CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s));
+  ensure_pool(x, bpl.sp.grid * bpl.sp.warps, n_tot, s);
   if (bpl.sp.hash_slots == 0) bpl.sp.grid = std::max(1, std::min(bpl.sp.grid, x->pool_size / bpl.sp.warps));   // one set per warp
 
   // batch schedule
@@ -352,8 +360,11 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   }
   int64_t done = n_old;
   if (done == 0) { x->entry = 0; x->max_layer = 0; done = 1; x->n = 1; }     // :774-778
-  // if a batch fails the index keeps the nodes linked so far: drop the bookkeeping of the rest
+  // if a batch fails the bookkeeping is cut back to the nodes linked so far, but the failed batch may
+  // already have prepended its nodes to existing rows: the index is marked unusable (search / insert
+  // refuse it) rather than left answering with ids that do not exist
   auto rollback = [&]() {
+    x->poisoned = true;
     x->h_level.resize((size_t)x->n);
     x->h_upper_off.resize((size_t)x->n);
     int64_t rows_kept = 0;
@@ -393,6 +404,7 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   x->st.build_n_dist = c[0];
   x->st.build_n_exp = c[1];
   x->st.build_visited_overflows = evs[0];
+  x->st.build_dropped_incoming = c[2];
   x->st.build_algorithmic_bytes = (double)c[0] * 4.0 * x->dim + (double)c[1] * 4.0 * x->slots0;
   x->st.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   x->last_nq = 0;

@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t row_id(const GraphView& g, uint32_t node, in
 template <int CPL>
 __device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* cand, int ncand, int want, int keep_all,
                                                  uint32_t* sel, float4* qe, float4* qs2, float* newd, int lane,
-                                                 uint32_t& n_dist) {
+                                                 uint32_t& n_dist, Stage* st = nullptr) {
   int nsel = 0;
   if (want <= 0) return 0;
   if (keep_all && ncand <= want) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* c
       load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)e * g.ld4, qe, qs2, lane);
       for (int base = 0; base < nsel; base += 8) {
         int cnt = min(8, nsel - base);
-        batch_dist<CPL>(g, qe, qs2, sel + base, newd, cnt, lane);
+        batch_dist<CPL>(g, qe, qs2, sel + base, newd, cnt, lane, st);
         n_dist += cnt;
         bool bad = lane < cnt && !(de < newd[lane]);
         unsigned any_bad = __ballot_sync(FULL, bad);
@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
   float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);
   uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);
+  stage_attach(w.st, reinterpret_cast<unsigned char*>(sel + bp.sel_cap), p.stage_slots, g.ld4, lane);
+  w.tie_spill = nullptr; w.tie_slot = -1;
   float4 qe[CPL > 0 ? CPL : 1];
 
   unsigned long long tot_dist = 0, tot_exp = 0;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     uint32_t cur = (uint32_t)g.entry;
     if (lane == 0) w.newid[0] = cur;
     __syncwarp();
-    batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, 1, lane);
+    batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, 1, lane, &w.st);
     float d_cur = w.newd[0];
     __syncwarp();
     for (int layer = g.max_layer; layer > lv; layer--) greedy_layer(g, w, layer, cur, d_cur, n_dist, n_expU);
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
       __syncwarp();
       // select_neighbours (MinQueue.copy w_queue) nc (:818-819)
       const int want = layer == 0 ? bp.sel0 : bp.selU;
-      int nsel = select_neighbours<CPL>(g, w.keys, n, want, bp.keep_all, sel, qe, qs2, w.newd, lane, n_dist);
+      int nsel = select_neighbours<CPL>(g, w.keys, n, want, bp.keep_all, sel, qe, qs2, w.newd, lane, n_dist, &w.st);
       // set_connections_for_new_node (:820): Neighbours.add prepends, so the row head is the
       // last node selected; the reverse half is deferred to the link phase
       int32_t* row = row_ptr(bp, row_id(g, v, layer));
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     }
     tot_dist += n_dist;
     tot_exp += n_exp0 + n_expU;
-    if (tie_overflow && lane == 0) atomicAdd(p.events + 1, 1ull);
+    if (tie_overflow && lane == 0) atomicAdd(p.events + 3, 1ull);
   }
   if (lane == 0) {
     atomicAdd(bp.counters + 0, tot_dist);
@@ -222,7 +224,7 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* in, uint64_t* out
 // Per-warp shared memory: ukey[ucap] u64, sorted[ucap] u64, uid[ucap] u32, ud[ucap] f32,
 // sel[sel_cap] u32, newd[32] f32, qs / qs2.
 __host__ __device__ inline int link_smem_per_warp(int ucap, int sel_cap, int q_chunks) {
-  return ucap * 8 * 2 + ucap * 4 * 2 + sel_cap * 4 + 32 * 4 + 2 * q_chunks * 16;
+  return ucap * 8 * 2 + ucap * 4 * 2 + sel_cap * 4 + 32 * 4 + 2 * q_chunks * 16;      // (+ the bulk-copy ring, when used)
 }
 
 template <int CPL>
@@ -239,6 +241,8 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
   float* ud = reinterpret_cast<float*>(uid + bp.ucap);
   uint32_t* sel = reinterpret_cast<uint32_t*>(ud + bp.ucap);
   float* newd = reinterpret_cast<float*>(sel + bp.sel_cap);
+  Stage st;
+  stage_attach(st, reinterpret_cast<unsigned char*>(newd + 32), bp.sp.stage_slots, g.ld4, lane);
   float4 qa[CPL > 0 ? CPL : 1], qe[CPL > 0 ? CPL : 1];
   const unsigned nheads = *bp.head_count;
   unsigned long long tot_dist = 0, tot_rows = 0, tot_dropped = 0;
@@ -292,12 +296,12 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
     }
     // min_queue_of_neighbours (:791-798): distances from the owner to every member
     load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)a * g.ld4, qa, qs, lane);
-    batch_dist<CPL>(g, qa, qs, uid, ud, u, lane);
+    batch_dist<CPL>(g, qa, qs, uid, ud, u, lane, &st);
     uint32_t n_dist = (uint32_t)u;
     for (int j = lane; j < u; j += 32) ukey[j] = make_key(ud[j], uid[j]);
     __syncwarp();
     warp_rank_sort(ukey, sorted, u, lane);
-    int nsel = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist);   // :824-826
+    int nsel = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist, &st);   // :824-826
     // Graph.set_connections (:182-196): the row becomes the selected list (head = last kept) ...
     for (int j = lane; j < slots; j += 32) row[j] = j < nsel ? (int32_t)sel[nsel - 1 - j] : -1;
     // ... and every member that fell out loses its link to the owner
@@ -381,6 +385,8 @@ __global__ void __launch_bounds__(32) build_link_seq_kernel(const BuildParams bp
   uint32_t* nbs = reinterpret_cast<uint32_t*>(newd + 32);       // the new node's list on this layer
   uint32_t* pend = nbs + bp.sel_cap;                            // 1: the node is logically at the head of that neighbour's full row
   uint32_t* rem = pend + bp.sel_cap;                            // dropped members of one pruned list
+  Stage st;
+  stage_attach(st, reinterpret_cast<unsigned char*>(rem + bp.sel_cap), bp.sp.stage_slots, g.ld4, lane);
   float4 qa[CPL > 0 ? CPL : 1], qe[CPL > 0 ? CPL : 1];
   const uint32_t v = (uint32_t)bp.n0;
   uint32_t n_dist = 0;
@@ -432,12 +438,12 @@ __global__ void __launch_bounds__(32) build_link_seq_kernel(const BuildParams bp
       __syncwarp();
       if (u <= nc) continue;                                              // :823
       load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)a * g.ld4, qa, qs, lane);
-      batch_dist<CPL>(g, CPL > 0 ? qa : nullptr, qs, uid, ud, u, lane);   // min_queue_of_neighbours (:791-798)
+      batch_dist<CPL>(g, CPL > 0 ? qa : nullptr, qs, uid, ud, u, lane, &st);   // min_queue_of_neighbours (:791-798)
       n_dist += u;
       for (int i = lane; i < u; i += 32) ukey[i] = make_key(ud[i], uid[i]);
       __syncwarp();
       warp_rank_sort(ukey, sorted, u, lane);
-      int ns = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist);   // :824-826
+      int ns = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist, &st);   // :824-826
       for (int i = lane; i < slots; i += 32) row[i] = i < ns ? (int32_t)sel[ns - 1 - i] : -1;   // Graph.set_connections step 1
       if (lane == 0) pend[j] = 0u;
       // step 2: removed = old \ new, walked in ascending id (Set.iter)

@@ -188,9 +188,14 @@ __device__ __forceinline__ void team_dist(const GraphView& g, const float4* q, c
 
 // ids[0..cnt) (shared) -> d[0..cnt) (shared).  cnt >= 1 is warp-uniform.  Rounds of eight
 // vectors (two per team) while more than four remain, then one round of up to four.
+struct Stage;
+__device__ __forceinline__ void batch_dist_staged(const GraphView& g, const float4* qs, const uint32_t* ids, float* d,
+                                                  int cnt, int lane, Stage& st);
+__device__ __forceinline__ bool stage_on(const Stage* st);
 template <int CPL>
 __device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, const float4* qs,
-                                           const uint32_t* ids, float* d, int cnt, int lane) {
+                                           const uint32_t* ids, float* d, int cnt, int lane, Stage* st = nullptr) {
+  if (CPL == 0 && stage_on(st)) { batch_dist_staged(g, qs, ids, d, cnt, lane, *st); return; }
   const int tl = lane & (TEAM - 1), team = lane >> 3;
   int base = 0;
   for (; base + 4 < cnt; base += 8) {
@@ -209,6 +214,104 @@ __device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, 
     if (tl == 0 && j0 < cnt) d[j0] = o[0];
   }
   __syncwarp();
+}
+
+// ---- high-dimension rows: bulk-copy (1-D TMA) staged gather ---------------------------------------
+// Rows of >= STAGE_MIN_BYTES (dim >= 256) are not fetched with per-lane LDG: one elected lane issues
+// one `cp.async.bulk` per row (a single UBLKCP instruction moves a whole 3 840-byte GIST row) into a
+// per-warp ring of `slots` rows in shared memory, each slot with its own mbarrier (complete_tx counts
+// the bytes), and the teams consume the rows from shared memory — four rows per round, one per
+// team — in the SAME summation order as the LDG path (SUM_TEAM8), so results stay bit-identical.
+// Every slot is refilled with the row `slots` places further on as soon as its round is done, so
+// `slots` rows (30 KB at 8 x 3 840 B) stay in flight per warp, against 4 KB for the LDG path.
+constexpr int STAGE_MIN_BYTES = 1024;
+constexpr int STAGE_MAX_SLOTS = 32;
+struct Stage {
+  float4* ring;        // slots rows of ld4 float4 each; null = rows are read with LDG
+  uint64_t* bar;       // [slots] mbarriers
+  int slots;
+  uint32_t parity;     // bit s = phase parity the next wait on slot s must observe (warp-uniform)
+};
+__device__ __forceinline__ bool stage_on(const Stage* st) { return st != nullptr && st->ring != nullptr; }
+__host__ __device__ inline int stage_smem_bytes(int slots, int ld4) { return slots * ld4 * 16 + ((slots * 8 + 15) & ~15); }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// lane 0 of every warp initialises its own barriers; the fences make them visible to the async proxy
+__device__ __forceinline__ void stage_init(Stage& st, float4* ring, uint64_t* bar, int slots, int lane) {
+  st.ring = ring; st.bar = bar; st.slots = slots; st.parity = 0u;
+  if (ring && lane == 0) {
+    for (int i = 0; i < slots; i++) mbar_init(bar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+}
+
+// batch_dist through the ring: ids[0..cnt) -> d[0..cnt).  Row j travels through slot j % slots; round
+// r evaluates rows 4r .. 4r+3, one per team.  The target is the shared copy qs.
+__device__ __forceinline__ void batch_dist_staged(const GraphView& g, const float4* qs, const uint32_t* ids, float* d,
+                                                  int cnt, int lane, Stage& st) {
+  const int tl = lane & (TEAM - 1), team = lane >> 3;
+  const bool dot = g.metric != 0;
+  const uint32_t row_bytes = (uint32_t)g.ld4 * 16u;
+  const int R = st.slots;
+  if (lane == 0) {
+    const int m = min(cnt, R);
+    for (int j = 0; j < m; j++) {
+      mbar_expect_tx(st.bar + j, row_bytes);
+      bulk_g2s(st.ring + (size_t)j * g.ld4, reinterpret_cast<const float4*>(g.vec) + (size_t)ids[j] * g.ld4, row_bytes, st.bar + j);
+    }
+  }
+  int slot0 = 0;                                   // slot of row `base`
+  for (int base = 0; base < cnt; base += 4) {
+    const int m = min(4, cnt - base);
+    int mine = slot0 + min(team, m - 1);           // teams beyond the tail re-read the last row of the round
+    if (mine >= R) mine -= R;
+    mbar_wait(st.bar + mine, (st.parity >> mine) & 1u);
+    const float4* row = st.ring + (size_t)mine * g.ld4;
+    float2 a0 = make_float2(0.f, 0.f);
+    int c = tl;
+    for (; c + 3 * TEAM < g.chunks; c += 4 * TEAM) {
+      float4 x[4], qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { x[u] = row[c + u * TEAM]; qq[u] = qs[c + u * TEAM]; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) a0 = acc4(a0, qq[u], x[u], dot);
+    }
+    for (; c < g.chunks; c += TEAM) a0 = acc4(a0, qs[c], row[c], dot);
+    const float o = finish_metric(team_reduce(a0), g.metric);
+    if (tl == 0 && team < m) d[base + team] = o;
+    __syncwarp();                                  // every lane is done with this round's rows
+    if (lane == 0) {                               // the freed slots take the rows `R` places further on
+      for (int i = 0; i < m; i++) {
+        const int j = base + R + i;
+        if (j >= cnt) break;
+        int sl = slot0 + i; if (sl >= R) sl -= R;
+        mbar_expect_tx(st.bar + sl, row_bytes);
+        bulk_g2s(st.ring + (size_t)sl * g.ld4, reinterpret_cast<const float4*>(g.vec) + (size_t)ids[j] * g.ld4, row_bytes, st.bar + sl);
+      }
+    }
+    for (int i = 0; i < m; i++) { int sl = slot0 + i; if (sl >= R) sl -= R; st.parity ^= 1u << sl; }
+    slot0 += m; if (slot0 >= R) slot0 -= R;
+  }
 }
 
 // ---- exact visited set ---------------------------------------------------------------------------

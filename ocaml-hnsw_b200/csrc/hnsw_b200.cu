@@ -94,7 +94,8 @@ struct hnswb200_index {
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // host-buffer search: copy / compute overlap
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
-  int64_t param_host_chunks = 0, param_strict_ties = 0;
+  int64_t param_host_chunks = 0;
+  int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
   unsigned int* h_ready = nullptr;      // pinned: the "pieces ready" values the copy stream writes after each piece
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
@@ -103,7 +104,11 @@ struct hnswb200_index {
   DevBuf<int> d_pool_busy;
   DevBuf<unsigned int> d_next;
   DevBuf<unsigned long long> d_events;
+  DevBuf<uint64_t> d_tie_pool;          // regions for tie lists that outgrow shared memory (search.cuh)
+  DevBuf<int> d_tie_busy;
   int pool_size = 0, pool_words = 0;
+  bool search_pending = false;          // ev1 marks the end of the last enqueued search (calls on one index are serialised on the device)
+  bool poisoned = false;                // a build batch failed half-way: the graph may hold links to nodes that do not exist
   // build scratch
   DevBuf<uint64_t> b_req, b_req_sorted, b_rem, b_rem_sorted;
   DevBuf<unsigned int> b_heads, b_ctr;
@@ -115,7 +120,7 @@ struct hnswb200_index {
   // stats
   hnswb200_stats st{};
   int64_t last_nq = 0;
-  int last_k = 0;
+  int last_k = 0, last_mode = 0;
   std::mutex mu;
 
   hb::GraphView view() const {
@@ -142,7 +147,9 @@ void init_device(hnswb200_index* x) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, x->device));
   x->num_sms = prop.multiProcessorCount;
   x->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-  CUDA_CHECK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+  // a BLOCKING stream: work enqueued on it is ordered after everything already enqueued on the legacy
+  // default stream (where a caller's copies and kernels usually run) and the other way round
+  CUDA_CHECK(cudaStreamCreateWithFlags(&x->stream, cudaStreamDefault));
   CUDA_CHECK(cudaEventCreate(&x->ev0));
   CUDA_CHECK(cudaEventCreate(&x->ev1));
 }
@@ -162,6 +169,7 @@ void upload_rows(float* dst, int ld, const float* src, int dim, int64_t n, cudaS
 // ---- search ---------------------------------------------------------------------------------------
 struct SearchPlan {
   int cpl, warps, ef_cap, hash_slots, q_chunks, smem_per_warp, grid, nb_cap;
+  int stage_slots;      // bulk-copy ring of this many rows per warp (0: LDG gathers)
   size_t smem;
 };
 
@@ -205,6 +213,15 @@ bool use_bitset_visited(const hnswb200_index* x, int ef, int smem_per_warp_hash,
   return smem_per_warp_hash > (227 * 1024) / 16 - 256 && clear_bytes <= 0.3 * query_bytes;
 }
 
+// High-dimension rows (>= 1 KB, dim >= 256) are gathered with one bulk copy per row into a per-warp
+// shared-memory ring (common.cuh, Stage).  Default depth: about 30 KB of rows in flight per warp
+// (8 GIST rows), at least one round of 4 and at most 16 rows.
+int stage_slots_for(const hnswb200_index* x, int cpl) {
+  if (cpl != 0 || x->ld * 4 < hb::STAGE_MIN_BYTES || x->param_stage_rows < 0) return 0;
+  if (x->param_stage_rows > 0) return (int)std::max<int64_t>(4, std::min<int64_t>(x->param_stage_rows, hb::STAGE_MAX_SLOTS));
+  return std::max(4, std::min(16, (30 * 1024) / (x->ld * 4)));
+}
+
 SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   SearchPlan pl;
   int chunks = x->ld / 4;
@@ -216,7 +233,9 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 42 * ef), 128);
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
-  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap);
+  pl.stage_slots = stage_slots_for(x, pl.cpl);
+  const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
+  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes;
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
   hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
   {
@@ -228,7 +247,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   }
   if (use_bitset_visited(x, ef, fixed + hs * 4, x->n)) hs = 0;
   pl.hash_slots = hs;
-  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks, pl.nb_cap);
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks, pl.nb_cap) + stage_bytes;
   // pack the SM: as many warps as shared memory and registers (64 per thread: 32 warps) allow, in CTAs of <= 4 warps
   int per_sm_warps = std::max(1, std::min(4 * HB_SEARCH_MINB, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 256))));
   if (x->param_max_warps_per_sm > 0) per_sm_warps = std::max(1, std::min<int>(per_sm_warps, (int)x->param_max_warps_per_sm));
@@ -259,7 +278,13 @@ void launch_search(const hb::SearchParams& p, const SearchPlan& pl, cudaStream_t
   CUDA_CHECK(cudaGetLastError());
 }
 
-void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
+constexpr int TIE_SLOTS = 32, TIE_CAP = 1 << 15;     // 32 regions of 32k keys (8 MB)
+void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes, cudaStream_t s) {
+  if (!x->d_tie_pool.p) {
+    x->d_tie_pool.reserve((size_t)TIE_SLOTS * TIE_CAP);
+    x->d_tie_busy.reserve(TIE_SLOTS);
+    CUDA_CHECK(cudaMemsetAsync(x->d_tie_busy.p, 0, TIE_SLOTS * sizeof(int), s));
+  }
   int words = (int)((n_nodes + 31) / 32);
   words = round_up(std::max(words, 1), 4);
   // a spilled query (or, for large beams, every warp) borrows one n-bit set; cap the pool at 4 GiB
@@ -268,9 +293,10 @@ void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes) {
   if (want > x->pool_size || words > x->pool_words) {
     x->d_bitpool.release();
     x->d_bitpool.reserve((size_t)want * words);
-    CUDA_CHECK(cudaMemsetAsync(x->d_bitpool.p, 0, (size_t)want * words * 4, x->stream));
+    // cleared on the stream the kernel is launched on (a memset on another stream is not ordered before it)
+    CUDA_CHECK(cudaMemsetAsync(x->d_bitpool.p, 0, (size_t)want * words * 4, s));
     x->d_pool_busy.reserve((size_t)want);
-    CUDA_CHECK(cudaMemsetAsync(x->d_pool_busy.p, 0, (size_t)x->d_pool_busy.n * sizeof(int), x->stream));
+    CUDA_CHECK(cudaMemsetAsync(x->d_pool_busy.p, 0, (size_t)x->d_pool_busy.n * sizeof(int), s));
     x->pool_size = want; x->pool_words = words;
   }
 }
@@ -290,6 +316,7 @@ void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
   if (nq < 0 || k <= 0) fail(HNSWB200_EINVAL, "search: nq must be >= 0 and k > 0");
   if (ef < k) fail(HNSWB200_EINVAL, "search: ef must be >= k");
   if (mode != HNSWB200_MODE_PARITY && mode != HNSWB200_MODE_FAST) fail(HNSWB200_EINVAL, "search: unknown mode");
+  if (x->poisoned) fail(HNSWB200_ECUDA, "the index is unusable: an earlier build/insert call failed half-way");
   if (x->n == 0 || x->entry < 0) fail(HNSWB200_EINVAL, "knn: empty hgraph");     // lib/ohnsw.ml:862
   if (ef > 4096) fail(HNSWB200_EINVAL, "search: ef > 4096 is not supported");
 }
@@ -306,13 +333,19 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp; p.nb_cap = pl.nb_cap;
+  p.stage_slots = pl.stage_slots;
   p.out_ids = d_ids; p.out_dists = d_dists; p.counters = counters;
   p.n_peer_out = n_peer;
   for (int r = 0; r < n_peer; r++) { p.peer_ids[r] = peer_ids[r]; p.peer_dists[r] = peer_dists[r]; }
   p.next_query = next; p.bitset_pool = x->d_bitpool.p; p.pool_busy = x->d_pool_busy.p;
   p.pool_size = x->pool_size; p.words = x->pool_words; p.events = x->d_events.p;
+  p.tie_pool = x->d_tie_pool.p; p.tie_busy = x->d_tie_busy.p; p.tie_slots = TIE_SLOTS; p.tie_cap = TIE_CAP;
   SearchPlan q = pl;
   q.grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (nq + pl.warps - 1) / pl.warps));
+  static const bool trace = std::getenv("HNSWB200_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "[hnsw_b200 search] nq=%lld ef=%d cpl=%d grid=%d x %d warps, %d B smem/warp (hash %d slots, ring %d rows), visited %s\n",
+            (long long)nq, ef, pl.cpl, q.grid, pl.warps, pl.smem_per_warp, pl.hash_slots, pl.stage_slots, pl.hash_slots ? "hash" : "bitset");
   switch (pl.cpl) {
     case 1: launch_search<1>(p, q, s); break;
     case 2: launch_search<2>(p, q, s); break;
@@ -325,13 +358,14 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
 
 void finish_search(hnswb200_index* x, const unsigned long long* evs, int mode) {
   x->st.search_visited_overflows = evs[0];
-  x->st.search_tie_overflows = evs[1];
-  // More than TIES_CAP evicted candidates at exactly the beam's top distance (many duplicate
-  // vectors): the surplus is not revisited.  The reference's own order among equal keys is
-  // unspecified (Core_kernel.Heap), so this is reported, and only an error on request.
-  if (evs[1] && mode == HNSWB200_MODE_PARITY && x->param_strict_ties)
-    fail(HNSWB200_ECUDA, "search: more than 32 equal-distance candidates at the beam boundary for " +
-                             std::to_string(evs[1]) + " queries (duplicate vectors?); parity cannot be guaranteed");
+  x->st.search_tie_spills = evs[1];
+  x->st.search_tie_overflows = evs[3];
+  // Evicted candidates at exactly the beam's top distance (duplicate vectors) stay poppable: 32 of
+  // them in shared memory, 32k more in a global region.  Beyond that — or when no region could be
+  // had — the surplus is not revisited and the result may differ from the reference's: an error.
+  if (evs[3] && mode == HNSWB200_MODE_PARITY)
+    fail(HNSWB200_ECUDA, "search: the list of equal-distance candidates at the beam boundary overflowed for " +
+                             std::to_string(evs[3]) + " queries (tens of thousands of duplicate vectors?); parity cannot be guaranteed");
 }
 
 void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
@@ -340,22 +374,27 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
   SearchPlan pl = plan_search(x, ef, nq);
-  ensure_pool(x, pl.grid * pl.warps, x->n);
-  if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));   // one set per warp
+  // the work counter, events and per-query counters are per-index scratch: a search enqueued on another
+  // stream waits for the previous one (calls on one index are serialised on the device as on the host)
+  if (x->search_pending) CUDA_CHECK(cudaStreamWaitEvent(s, x->ev1, 0));
   x->d_counters.reserve((size_t)nq * 3);
   x->d_next.reserve(8);
   x->d_events.reserve(4);
+  ensure_pool(x, pl.grid * pl.warps, x->n, s);
+  if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));   // one set per warp
   CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, sizeof(unsigned int), s));
   CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s));
   CUDA_CHECK(cudaEventRecord(x->ev0, s));
   enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists);
   CUDA_CHECK(cudaEventRecord(x->ev1, s));
+  x->search_pending = true;
   x->last_nq = nq;
   x->last_k = k;
+  x->last_mode = mode;
   x->st.search_queries = (uint64_t)nq;
   if (own_stream) {
     CUDA_CHECK(cudaStreamSynchronize(s));
-    unsigned long long evs[2];
+    unsigned long long evs[4];
     CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
     finish_search(x, evs, mode);
   }
@@ -370,7 +409,8 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
   SearchPlan pl = plan_search(x, ef, nq);
-  ensure_pool(x, pl.grid * pl.warps, x->n);
+  if (x->search_pending) CUDA_CHECK(cudaStreamWaitEvent(x->stream, x->ev1, 0));
+  ensure_pool(x, pl.grid * pl.warps, x->n, x->stream);
   if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));
   int C = x->param_host_chunks >= 2 ? (int)std::min<int64_t>(x->param_host_chunks, HOST_CHUNKS) : 1;
   if (nq < 4096) C = 1;
@@ -416,9 +456,11 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   CUDA_CHECK(cudaEventRecord(x->ev1, s0));
   if (ids) CUDA_CHECK(cudaMemcpyAsync(ids, x->d_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
   CUDA_CHECK(cudaMemcpyAsync(dists, x->d_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
-  CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
+  CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
+  x->search_pending = true;
   x->last_nq = nq;
   x->last_k = k;
+  x->last_mode = mode;
   x->st.search_queries = (uint64_t)nq;
   CUDA_CHECK(cudaStreamSynchronize(s0));
   if (C > 1) CUDA_CHECK(cudaStreamSynchronize(x->aux_stream[0]));
@@ -566,7 +608,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "max_warps_per_sm") x->param_max_warps_per_sm = value;
     else if (s == "visited_mode") x->param_visited_mode = value;
     else if (s == "host_chunks") x->param_host_chunks = value;
-    else if (s == "strict_ties") x->param_strict_ties = value;
+    else if (s == "stage_rows") x->param_stage_rows = value;
     else if (s == "row_floats") {             // vector row stride in floats (multiple of 4, >= dim); only on an empty index
       if (x->n != 0) fail(HNSWB200_EINVAL, "row_floats can only be set on an empty index");
       if (value < x->dim || value % 4 != 0) fail(HNSWB200_EINVAL, "row_floats must be a multiple of 4 and >= dim");
@@ -702,6 +744,10 @@ int hnswb200_get_stats(hnswb200_index* x, hnswb200_stats* out) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, x->ev0, x->ev1) == cudaSuccess) st.search_kernel_ms = ms;
       else cudaGetLastError();
+      // a search that was only enqueued on a caller's stream never went through finish_search
+      unsigned long long evs[4];
+      CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
+      st.search_visited_overflows = evs[0]; st.search_tie_spills = evs[1]; st.search_tie_overflows = evs[3];
     }
     // lib/hnsw.ml:732-751 counts distance calls; bytes per SURVEY.md 8d
     st.search_algorithmic_bytes = (double)st.search_n_dist * 4.0 * x->dim + (double)st.search_n_exp0 * 4.0 * x->slots0 +

@@ -37,6 +37,7 @@ struct SearchParams {
   int hash_slots;            // multiple of 4
   int nb_cap;                // list slots gathered per pass: 32 or 64 (staging arrays hold this many)
   int q_smem_chunks;         // float4 slots reserved for the query copy
+  int stage_slots;           // > 0: rows are staged through a per-warp bulk-copy ring of this many rows (common.cuh)
   int smem_per_warp;
   int32_t* out_ids;          // [nq][k] or null
   float* out_dists;          // [nq][k]
@@ -51,7 +52,12 @@ struct SearchParams {
   int* pool_busy;
   int pool_size;
   int words;
-  unsigned long long* events; // [0] visited spills, [1] tie-list overflows, [2] warps that gave up waiting for queries
+  unsigned long long* events; // [0] visited spills, [1] tie lists that left shared memory, [2] warps that gave up waiting for queries,
+                              // [3] tie lists that outgrew their global region too (the only way PARITY can degrade)
+  // evicted candidates tied with the beam's top beyond TIES_CAP continue in a region of this pool
+  uint64_t* tie_pool;        // [tie_slots][tie_cap]
+  int* tie_busy;
+  int tie_slots, tie_cap;
   // streamed queries (host-buffer call): the batch arrives in pieces of `ready_step` queries while the
   // kernel runs; *ready = pieces copied so far (written by the copy stream after each piece)
   const unsigned int* ready;
@@ -60,6 +66,12 @@ struct SearchParams {
 
 __host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, int q_chunks, int nb_cap = 32) {
   return ef_cap * 8 + TIES_CAP * 8 + nb_cap * 4 + nb_cap * 4 + q_chunks * 16 + hash_slots * 4;
+}
+// the bulk-copy ring (when used) follows the fixed part of the warp's block
+__device__ __forceinline__ void stage_attach(Stage& st, unsigned char* at, int slots, int ld4, int lane) {
+  float4* ring = slots > 0 ? reinterpret_cast<float4*>(at) : nullptr;
+  uint64_t* bar = slots > 0 ? reinterpret_cast<uint64_t*>(at + (size_t)slots * ld4 * 16) : nullptr;
+  stage_init(st, ring, bar, slots, lane);
 }
 
 // QREG: the target vector lives in registers (CPL float4 per lane); otherwise in shared memory
@@ -73,6 +85,9 @@ struct WarpCtx {
   float4* qs;
   float4 q[(CPL > 0 && QREG) ? CPL : 1];
   VisitedSet vis;
+  Stage st;
+  uint64_t* tie_spill;       // non-null while this warp holds a region of the tie pool
+  int tie_slot;
   int lane;
   __device__ __forceinline__ const float4* target_regs() const { return (CPL > 0 && QREG) ? q : nullptr; }
 };
@@ -129,6 +144,41 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id)
   return hash_test_and_set(v.tab, v.slots, id);
 }
 
+// ---- the tie list: evicted candidates whose distance equals the beam's top ------------------------
+// Entries 0..TIES_CAP-1 live in shared memory, later ones in a region borrowed from a global pool,
+// so the list never drops an entry the reference's visit_me queue would still pop (:565-568).
+template <class W>
+__device__ __forceinline__ uint64_t tie_get(const W& w, int i) { return i < TIES_CAP ? w.ties[i] : __ldcg(w.tie_spill + (i - TIES_CAP)); }
+template <class W>
+__device__ __forceinline__ void tie_set(W& w, int i, uint64_t v) { if (i < TIES_CAP) w.ties[i] = v; else __stcg(w.tie_spill + (i - TIES_CAP), v); }
+// borrow a region (bounded wait: a region is held for the rest of one layer search only); false if none could be had
+template <class W>
+__device__ __forceinline__ bool tie_borrow(W& w, const SearchParams& p, int lane) {
+  int s = -1;
+  if (lane == 0 && p.tie_slots > 0) {
+    unsigned i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % (unsigned)p.tie_slots;
+    for (unsigned tries = 0; tries < (1u << 22); tries++) {
+      if (atomicCAS(&p.tie_busy[i], 0, 1) == 0) { s = (int)i; break; }
+      i = i + 1 == (unsigned)p.tie_slots ? 0 : i + 1;
+      if ((tries & 31) == 31) __nanosleep(100);
+    }
+    if (s >= 0) { __threadfence(); atomicAdd(p.events + 1, 1ull); }
+  }
+  s = __shfl_sync(FULL, s, 0);
+  if (s < 0) return false;
+  w.tie_slot = s;
+  w.tie_spill = p.tie_pool + (size_t)s * p.tie_cap;
+  return true;
+}
+template <class W>
+__device__ __forceinline__ void tie_release(W& w, const SearchParams& p, int lane) {
+  if (!w.tie_spill) return;
+  __syncwarp();
+  __threadfence();
+  if (lane == 0) atomicExch(&p.tie_busy[w.tie_slot], 0);
+  w.tie_spill = nullptr;
+}
+
 // search_k (lib/ohnsw.ml:543-588) on layer `layer`, beam already seeded with `n` keys (all
 // unexpanded, all marked visited).  Leaves the nearest set in keys[0..n).
 template <int CPL, bool QREG>
@@ -162,21 +212,27 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
     uint64_t ck = pos >= 0 ? w.keys[pos] : KEY_INF;
     bool from_ties = false;
     if (ties_n > 0) {
-      uint64_t tk = lane < ties_n ? w.ties[lane] : KEY_INF;
-      uint64_t mn = tk;
+      uint64_t mn = KEY_INF;
+      for (int b = 0; b < ties_n; b += 32) {
+        const uint64_t tk = b + lane < ties_n ? tie_get(w, b + lane) : KEY_INF;
+        mn = tk < mn ? tk : mn;
+      }
       for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }
       if (mn < ck) {
-        unsigned who = __ballot_sync(FULL, tk == mn);
-        int sel = __ffs(who) - 1;
-        uint64_t lastk = w.ties[ties_n - 1];
+        int sel = 0;
+        for (int b = 0; b < ties_n; b += 32) {                 // keys are distinct: exactly one entry matches
+          const unsigned who = __ballot_sync(FULL, b + lane < ties_n && tie_get(w, b + lane) == mn);
+          if (who) { sel = b + __ffs(who) - 1; break; }
+        }
+        const uint64_t lastk = tie_get(w, ties_n - 1);
         __syncwarp();
-        if (lane == 0) w.ties[sel] = lastk;
+        if (lane == 0) tie_set(w, sel, lastk);
         ties_n--;
         ck = mn; from_ties = true;
         __syncwarp();
       }
     }
-    if (ck == KEY_INF) break;                      // visit_me empty (:566) or only dead entries (:568)
+    if (ck == KEY_INF) break;                      // visit_me empty (:566)
     if (!from_ties) {
       if (lane == 0) w.keys[pos] = ck | 1ull;
       fu = pos + 1;
@@ -214,11 +270,11 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
         // every vector beyond the first round of eight starts moving towards L2 now, so the
         // later rounds of batch_dist wait for L2, not for HBM
         for (int j = lane; j < total; j += 32)
-          if (j >= 8) {
+          if (j >= (w.st.ring ? w.st.slots : 8)) {
             const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[j] * g.ld4 * 16;
             for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
           }
-        batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, total, lane);        // MinQueue.element (:573)
+        batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, total, lane, &w.st);   // MinQueue.element (:573)
         n_dist += total;
       }
       for (int g0 = 0; g0 < total; g0 += 32) {
@@ -297,10 +353,12 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
               const bool t2 = acc && f >= ef && t == new_top;
               const unsigned m1 = __ballot_sync(FULL, t1), m2 = __ballot_sync(FULL, t2);
               const int c1 = __popc(m1), c2 = __popc(m2);
-              if (ties_n + c1 + c2 > TIES_CAP) tie_overflow = true;
+              bool room = ties_n + c1 + c2 <= TIES_CAP;
+              if (!room) room = (w.tie_spill || tie_borrow(w, p, lane)) && ties_n + c1 + c2 <= TIES_CAP + p.tie_cap;
+              if (!room) tie_overflow = true;
               else {
-                if (t1) w.ties[ties_n + __popc(m1 & ((1u << lane) - 1u))] = ev_key;
-                if (t2) w.ties[ties_n + c1 + __popc(m2 & ((1u << lane) - 1u))] = key;
+                if (t1) tie_set(w, ties_n + __popc(m1 & ((1u << lane) - 1u)), ev_key);
+                if (t2) tie_set(w, ties_n + c1 + __popc(m2 & ((1u << lane) - 1u)), key);
                 ties_n += c1 + c2;
               }
               __syncwarp();
@@ -311,6 +369,7 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
       if (row_ended) break;
     }
   }
+  tie_release(w, p, lane);
 }
 
 
@@ -361,7 +420,7 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL, QR
       if (!cnt) break;
       if (nb >= 0) w.newid[__popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
       __syncwarp();
-      batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, cnt, lane);
+      batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, cnt, lane, &w.st);
       n_dist += cnt;
       uint64_t mine = lane < cnt ? (((uint64_t)f2ord(w.newd[lane]) << 32) | (uint32_t)(r0 + lane)) : KEY_INF;
       uint64_t mn = mine;
@@ -397,6 +456,8 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
   w.newd = reinterpret_cast<float*>(w.newid + p.nb_cap);
   w.qs = reinterpret_cast<float4*>(w.newd + p.nb_cap);
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
+  stage_attach(w.st, reinterpret_cast<unsigned char*>(w.vis.tab + p.hash_slots), p.stage_slots, g.ld4, lane);
+  w.tie_spill = nullptr; w.tie_slot = -1;
 
   while (true) {
     unsigned qi = 0;
@@ -430,7 +491,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     uint32_t cur = (uint32_t)g.entry;
     if (lane == 0) w.newid[0] = cur;
     __syncwarp();
-    batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, 1, lane);
+    batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, 1, lane, &w.st);
     float d_cur = w.newd[0];
     __syncwarp();
     for (int layer = g.max_layer; layer >= 1; layer--) greedy_layer(g, w, layer, cur, d_cur, n_dist, n_expU);
@@ -467,7 +528,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
         p.counters[(size_t)qi * 3 + 1] = n_exp0;
         p.counters[(size_t)qi * 3 + 2] = n_expU;
       }
-      if (tie_overflow) atomicAdd(p.events + 1, 1ull);
+      if (tie_overflow) atomicAdd(p.events + 3, 1ull);
     }
     visited_release(w.vis, p, lane);
     __syncwarp();

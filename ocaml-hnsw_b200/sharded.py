@@ -116,7 +116,10 @@ class ShardedHgraph:
         import torch
         nq = q_dev.shape[0]
         b = self._buffers(nq, k)
-        stream = torch.cuda.current_stream().cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "the index's own stream, synchronous":
+        # name the legacy default stream explicitly (cudaStreamLegacy = 1) so the call only enqueues, in order
+        # with the caller's copies and with the barrier / merge that follow on the same stream
+        stream = torch.cuda.current_stream().cuda_stream or 1
         if self.world == 1:
             self.local.search_device(q_dev.data_ptr(), nq, k, k if ef is None else ef, b["ids"].data_ptr(), b["d"].data_ptr(),
                                      stream=stream, mode=mode)
@@ -127,7 +130,7 @@ class ShardedHgraph:
             pb = self._peer[self._step & 1]
             self._step += 1
             capi.check(capi.lib().hnswb200_search_device_multi(self.local._h, q_dev.data_ptr(), nq, k, k if ef is None else ef,
-                                                               mode, self.world, pb["ids_ptrs"], pb["d_ptrs"], stream or None))
+                                                               mode, self.world, pb["ids_ptrs"], pb["d_ptrs"], stream))
             pb["hdl"].barrier(channel=0)
             g = pb["t"]
         else:
@@ -137,7 +140,7 @@ class ShardedHgraph:
             dist.all_gather_into_tensor(g.view(self.world * 2, nq, k), b["packed"], group=self.group)
         capi.check(capi.lib().hnswb200_merge_topk_device(g.data_ptr(), g.data_ptr() + nq * k * 4, self.world, nq, k,
                                                          2 * nq * k, capi.ptr(self.offsets), b["out_ids"].data_ptr(),
-                                                         b["out_d"].data_ptr(), stream or None))
+                                                         b["out_d"].data_ptr(), stream))
         return b["out_ids"], b["out_d"]
 
     def knn_batch_bigarray(self, batch, *, k, ef=None, mode=capi.MODE_PARITY, out=None):

@@ -296,3 +296,73 @@ def test_build_argument_errors():
     capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), 10, None))
     with pytest.raises(ValueError, match="not empty"):
         capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), 10, None))
+
+
+def test_benchmark_ml_literal_shape_sequential_build():
+    """benchmark/benchmark.ml:115-128 as written (dim 784, M = 15, efConstruction = 400, uniform data), in
+    sequential mode: the GPU-built graph is the oracle's edge for edge.  Exercises 30- / 15-slot rows and
+    the bulk-copy staged gather inside the insert search, the selection heuristic and the link kernel.
+    (N = 1500 of the default 5000 keeps 1500 one-insert launch chains within the test budget.)"""
+    n, dim, M, efC = 1500, 784, 15, 400
+    X = uniform(n, dim, 1234)
+    lv = draw_levels(n, M)
+    lv[0] = 0
+    o = O.VecOracle(dim).build(X, M, efC, lv)
+    h = Ohnsw.Hgraph(dim, Ohnsw.distance_l2, M, efC)
+    h.set_param("build_batch", 1)
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), n, capi.ptr(lv)))
+    _same_graph(h.export_graph(), o.export())
+
+
+def test_benchmark_ml_literal_shape_batched_build():
+    """Same shape at the literal N = 5000, batched build: structure, search parity on the built graph, and
+    recall@10 at the reference's own beam (ef = k = 10) and wider, against the oracle-built index."""
+    n, dim, M, efC = 5000, 784, 15, 400
+    X, Q = uniform(n, dim, 1234), uniform(200, dim, 4321)
+    lv = draw_levels(n, M)
+    lv[0] = 0
+    h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=M, num_nodes_search_construction=efC, levels=lv)
+    g = h.export_graph()
+    _check_structure(g, lv, M)
+    o2 = _to_oracle(X, g)
+    o = O.VecOracle(dim).build(X, M, efC, lv)
+    gt, _ = O.bruteforce(X, Q, 10)
+    for ef in (10, 100):
+        ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=ef)
+        ids_2, d_2 = o2.search(Q, 10, ef)
+        assert_same_results(ids_g, d_g, ids_2, d_2)
+        ids_o, _ = o.search(Q, 10, ef)
+        assert abs(H.Recall.ids(gt, ids_g) - H.Recall.ids(gt, ids_o)) <= 0.03      # 200 queries on uniform 784-d data: loose
+
+
+@pytest.fixture(scope="module")
+def built100k():
+    """100k x 128 SIFT-like, M = 16, efConstruction = 200 (the bench's parameters at 1/10 of its rows): the GPU's
+    batched build runs ~70 batches up to n/64 nodes — the regime where batch members not seeing each
+    other matters — against the oracle's sequential build on identical inputs and levels."""
+    n, M, efC = 100_000, 16, 200
+    X = H.sift_like(n, 128, seed=1234)
+    Q = H.sift_like(5000, 128, seed=4321)
+    lv = draw_levels(n, M)
+    h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=M, num_nodes_search_construction=efC, levels=lv)
+    o = O.VecOracle(128).build(X, M, efC, lv)
+    gt_ids, gt_d = H.brute_force_knn_l2(X, Q, 10, return_ids=True)
+    return X, Q, lv, h, o, gt_ids, gt_d
+
+
+@pytest.mark.parametrize("ef", [16, 41, 128])
+def test_100k_batched_build_recall_two_sided(built100k, ef):
+    X, Q, lv, h, o, gt_ids, gt_d = built100k
+    ids_g, d_g = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=ef)
+    ids_o, d_o = o.search_mt(Q, 10, ef)[:2]
+    r_g, r_o = H.Recall.ids(gt_ids, ids_g), H.Recall.ids(gt_ids, ids_o)
+    assert abs(r_g - r_o) <= 0.005, f"ef={ef}: GPU-built recall@10 {r_g:.4f} vs oracle-built {r_o:.4f}"
+    c_g, c_o = H.Recall.compute(gt_d, d_g, 1e-4), H.Recall.compute(gt_d, d_o, 1e-4)
+    assert abs(c_g - c_o) <= 0.005
+
+
+def test_100k_batched_build_drops_no_incoming_link(built100k):
+    X, Q, lv, h, o, _, _ = built100k
+    st = h.stats()
+    assert st.build_dropped_incoming == 0       # rows that received more than LINK_MCAP new nodes in one batch
+    _check_structure(h.export_graph(), lv, 16)
