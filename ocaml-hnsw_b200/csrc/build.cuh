@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
   float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);
   uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);
-  stage_attach(w.st, reinterpret_cast<unsigned char*>(sel + bp.sel_cap), p.stage_slots, g.ld4, lane);
+  stage_attach(w.st, reinterpret_cast<unsigned char*>(sel + bp.sel_cap), p.stage_slots, p.stage_ahead, g.ld4, lane);
   w.tie_spill = nullptr; w.tie_slot = -1;
   float4 qe[CPL > 0 ? CPL : 1];
 
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
   uint32_t* sel = reinterpret_cast<uint32_t*>(ud + bp.ucap);
   float* newd = reinterpret_cast<float*>(sel + bp.sel_cap);
   Stage st;
-  stage_attach(st, reinterpret_cast<unsigned char*>(newd + 32), bp.sp.stage_slots, g.ld4, lane);
+  stage_attach(st, reinterpret_cast<unsigned char*>(newd + 32), bp.sp.stage_slots, bp.sp.stage_ahead, g.ld4, lane);
   float4 qa[CPL > 0 ? CPL : 1], qe[CPL > 0 ? CPL : 1];
   const unsigned nheads = *bp.head_count;
   unsigned long long tot_dist = 0, tot_rows = 0, tot_dropped = 0;
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(32) build_link_seq_kernel(const BuildParams bp
   uint32_t* pend = nbs + bp.sel_cap;                            // 1: the node is logically at the head of that neighbour's full row
   uint32_t* rem = pend + bp.sel_cap;                            // dropped members of one pruned list
   Stage st;
-  stage_attach(st, reinterpret_cast<unsigned char*>(rem + bp.sel_cap), bp.sp.stage_slots, g.ld4, lane);
+  stage_attach(st, reinterpret_cast<unsigned char*>(rem + bp.sel_cap), bp.sp.stage_slots, bp.sp.stage_ahead, g.ld4, lane);
   float4 qa[CPL > 0 ? CPL : 1], qe[CPL > 0 ? CPL : 1];
   const uint32_t v = (uint32_t)bp.n0;
   uint32_t n_dist = 0;

@@ -230,6 +230,8 @@ struct Stage {
   float4* ring;        // slots rows of ld4 float4 each; null = rows are read with LDG
   uint64_t* bar;       // [slots] mbarriers
   int slots;
+  int ahead;           // rows beyond the ring that are sent for with a bulk L2 prefetch (bounded: unbounded
+                       // look-ahead of 100 KB per warp x 1000 warps evicts the rows from L2 before they are used)
   uint32_t parity;     // bit s = phase parity the next wait on slot s must observe (warp-uniform)
 };
 __device__ __forceinline__ bool stage_on(const Stage* st) { return st != nullptr && st->ring != nullptr; }
@@ -250,13 +252,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 // lane 0 of every warp initialises its own barriers; the fences make them visible to the async proxy
-__device__ __forceinline__ void stage_init(Stage& st, float4* ring, uint64_t* bar, int slots, int lane) {
-  st.ring = ring; st.bar = bar; st.slots = slots; st.parity = 0u;
+__device__ __forceinline__ void stage_init(Stage& st, float4* ring, uint64_t* bar, int slots, int ahead, int lane) {
+  st.ring = ring; st.bar = bar; st.slots = slots; st.ahead = ahead; st.parity = 0u;
   if (ring && lane == 0) {
     for (int i = 0; i < slots; i++) mbar_init(bar + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -279,6 +284,8 @@ __device__ __forceinline__ void batch_dist_staged(const GraphView& g, const floa
       mbar_expect_tx(st.bar + j, row_bytes);
       bulk_g2s(st.ring + (size_t)j * g.ld4, reinterpret_cast<const float4*>(g.vec) + (size_t)ids[j] * g.ld4, row_bytes, st.bar + j);
     }
+  } else if (lane <= st.ahead && R + lane - 1 < cnt) {        // rows R .. R+ahead-1 start moving towards L2
+    bulk_prefetch_l2(reinterpret_cast<const float4*>(g.vec) + (size_t)ids[R + lane - 1] * g.ld4, row_bytes);
   }
   int slot0 = 0;                                   // slot of row `base`
   for (int base = 0; base < cnt; base += 4) {
@@ -308,6 +315,9 @@ __device__ __forceinline__ void batch_dist_staged(const GraphView& g, const floa
         mbar_expect_tx(st.bar + sl, row_bytes);
         bulk_g2s(st.ring + (size_t)sl * g.ld4, reinterpret_cast<const float4*>(g.vec) + (size_t)ids[j] * g.ld4, row_bytes, st.bar + sl);
       }
+    } else if (lane <= m && st.ahead > 0) {        // and the look-ahead window moves on by as many rows
+      const int j = base + R + st.ahead + lane - 1;
+      if (j < cnt) bulk_prefetch_l2(reinterpret_cast<const float4*>(g.vec) + (size_t)ids[j] * g.ld4, row_bytes);
     }
     for (int i = 0; i < m; i++) { int sl = slot0 + i; if (sl >= R) sl -= R; st.parity ^= 1u << sl; }
     slot0 += m; if (slot0 >= R) slot0 -= R;

@@ -96,6 +96,7 @@ struct hnswb200_index {
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t param_host_chunks = 0;
   int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
+  int64_t param_stage_ahead = -1;       // rows beyond the ring prefetched to L2 (-1 auto, 0..31)
   unsigned int* h_ready = nullptr;      // pinned: the "pieces ready" values the copy stream writes after each piece
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
@@ -222,6 +223,10 @@ int stage_slots_for(const hnswb200_index* x, int cpl) {
   return std::max(4, std::min(16, (30 * 1024) / (x->ld * 4)));
 }
 
+int stage_ahead_for(const hnswb200_index* x) {
+  return x->param_stage_ahead >= 0 ? (int)std::min<int64_t>(x->param_stage_ahead, 31) : 8;
+}
+
 SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   SearchPlan pl;
   int chunks = x->ld / 4;
@@ -248,10 +253,26 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   if (use_bitset_visited(x, ef, fixed + hs * 4, x->n)) hs = 0;
   pl.hash_slots = hs;
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks, pl.nb_cap) + stage_bytes;
+  // A batch small enough to be resident all at once (one warp per query, nq <= SMs x warps per SM) gets the
+  // deepest ring with which it still is: every query then runs from the first cycle, in CTAs of one warp so
+  // the SMs hold the same number of queries (1 000 GIST queries: 7 per SM with a 6-row ring).
+  bool one_wave = false;
+  if (pl.stage_slots && x->param_stage_rows == 0) {
+    const int64_t per_sm = (nq + x->num_sms - 1) / x->num_sms;
+    const int other = pl.smem_per_warp - stage_bytes, row_bytes = x->ld * 4;
+    if (per_sm <= 4 * HB_SEARCH_MINB) {
+      const int fit = (int)(((int64_t)(227 * 1024) / per_sm - 1024 - other - 8 * hb::STAGE_MAX_SLOTS) / row_bytes);
+      if (fit >= 4) {
+        one_wave = true;
+        pl.stage_slots = std::min(fit, 16);
+        pl.smem_per_warp = other + hb::stage_smem_bytes(pl.stage_slots, chunks);
+      }
+    }
+  }
   // pack the SM: as many warps as shared memory and registers (64 per thread: 32 warps) allow, in CTAs of <= 4 warps
   int per_sm_warps = std::max(1, std::min(4 * HB_SEARCH_MINB, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 256))));
   if (x->param_max_warps_per_sm > 0) per_sm_warps = std::max(1, std::min<int>(per_sm_warps, (int)x->param_max_warps_per_sm));
-  int warps = x->param_warps_per_cta > 0 ? (int)std::min<int64_t>(x->param_warps_per_cta, 4) : 0;
+  int warps = x->param_warps_per_cta > 0 ? (int)std::min<int64_t>(x->param_warps_per_cta, 4) : (one_wave ? 1 : 0);
   if (warps <= 0) {                                   // CTA shape that keeps the most warps resident (1 KB reserved per CTA)
     int best = 0;
     for (int w = 4; w >= 1; w--) {
@@ -334,6 +355,7 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp; p.nb_cap = pl.nb_cap;
   p.stage_slots = pl.stage_slots;
+  p.stage_ahead = stage_ahead_for(x);
   p.out_ids = d_ids; p.out_dists = d_dists; p.counters = counters;
   p.n_peer_out = n_peer;
   for (int r = 0; r < n_peer; r++) { p.peer_ids[r] = peer_ids[r]; p.peer_dists[r] = peer_dists[r]; }
@@ -609,6 +631,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "visited_mode") x->param_visited_mode = value;
     else if (s == "host_chunks") x->param_host_chunks = value;
     else if (s == "stage_rows") x->param_stage_rows = value;
+    else if (s == "stage_ahead") x->param_stage_ahead = value;
     else if (s == "row_floats") {             // vector row stride in floats (multiple of 4, >= dim); only on an empty index
       if (x->n != 0) fail(HNSWB200_EINVAL, "row_floats can only be set on an empty index");
       if (value < x->dim || value % 4 != 0) fail(HNSWB200_EINVAL, "row_floats must be a multiple of 4 and >= dim");

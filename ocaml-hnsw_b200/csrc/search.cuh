@@ -38,6 +38,7 @@ struct SearchParams {
   int nb_cap;                // list slots gathered per pass: 32 or 64 (staging arrays hold this many)
   int q_smem_chunks;         // float4 slots reserved for the query copy
   int stage_slots;           // > 0: rows are staged through a per-warp bulk-copy ring of this many rows (common.cuh)
+  int stage_ahead;           // rows beyond the ring prefetched to L2
   int smem_per_warp;
   int32_t* out_ids;          // [nq][k] or null
   float* out_dists;          // [nq][k]
@@ -68,10 +69,10 @@ __host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, 
   return ef_cap * 8 + TIES_CAP * 8 + nb_cap * 4 + nb_cap * 4 + q_chunks * 16 + hash_slots * 4;
 }
 // the bulk-copy ring (when used) follows the fixed part of the warp's block
-__device__ __forceinline__ void stage_attach(Stage& st, unsigned char* at, int slots, int ld4, int lane) {
+__device__ __forceinline__ void stage_attach(Stage& st, unsigned char* at, int slots, int ahead, int ld4, int lane) {
   float4* ring = slots > 0 ? reinterpret_cast<float4*>(at) : nullptr;
   uint64_t* bar = slots > 0 ? reinterpret_cast<uint64_t*>(at + (size_t)slots * ld4 * 16) : nullptr;
-  stage_init(st, ring, bar, slots, lane);
+  stage_init(st, ring, bar, slots, ahead, lane);
 }
 
 // QREG: the target vector lives in registers (CPL float4 per lane); otherwise in shared memory
@@ -269,8 +270,8 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
       if (total) {
         // every vector beyond the first round of eight starts moving towards L2 now, so the
         // later rounds of batch_dist wait for L2, not for HBM
-        for (int j = lane; j < total; j += 32)
-          if (j >= (w.st.ring ? w.st.slots : 8)) {
+        for (int j = lane; j < total && !w.st.ring; j += 32)
+          if (j >= 8) {
             const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[j] * g.ld4 * 16;
             for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
           }
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
   w.newd = reinterpret_cast<float*>(w.newid + p.nb_cap);
   w.qs = reinterpret_cast<float4*>(w.newd + p.nb_cap);
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
-  stage_attach(w.st, reinterpret_cast<unsigned char*>(w.vis.tab + p.hash_slots), p.stage_slots, g.ld4, lane);
+  stage_attach(w.st, reinterpret_cast<unsigned char*>(w.vis.tab + p.hash_slots), p.stage_slots, p.stage_ahead, g.ld4, lane);
   w.tie_spill = nullptr; w.tie_slot = -1;
 
   while (true) {

@@ -68,6 +68,9 @@ while hi is not None and hi - lo > 1:
         lo = mid
 ef_star = hi or bench.EF_SWEEP[-1]
 print(f"ef* = {ef_star}", flush=True)
+Ohnsw.knn_batch_bigarray(h, Q, k=a.k, ef=ef_star)
+c = h.last_search_counters(a.nq)[:, 0].astype(np.float64)
+print(f"ndist per query: mean {c.mean():.0f} p50 {np.percentile(c, 50):.0f} p99 {np.percentile(c, 99):.0f} max {c.max():.0f} (max/mean {c.max() / c.mean():.2f})", flush=True)
 
 
 def run(reps=5):
@@ -80,9 +83,10 @@ def run(reps=5):
 
 
 known = ("stage_rows", "max_warps_per_sm", "visited_mode", "hash_slots", "warps_per_cta")
+defaults = {"stage_ahead": -1}
 for setting in [{}] + settings:
-    for name in known:
-        h.set_param(name, setting.get(name, 0))
+    for name in known + tuple(defaults):
+        h.set_param(name, setting.get(name, defaults.get(name, 0)))
     ms, avg, s = run()
     gbs = s.search_algorithmic_bytes / ms / 1e6
     print(f"{setting or 'default'}: kernel_ms min {ms:.3f} avg {avg:.3f}  {gbs:.0f} GB/s  frac {gbs / 6553:.3f}  "

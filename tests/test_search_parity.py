@@ -232,19 +232,48 @@ def test_heavy_duplicates_are_exact():
         st = h.stats()
         spills += st.search_tie_spills
         assert st.search_tie_overflows == 0
-    # duplicates of one point, linked among themselves, with the accept-ties rule: every copy ties
-    Xd = np.concatenate([np.repeat(base[:1], 600, axis=0), uniform(300, 16, 10)]).astype(np.float32)
-    Xd = Xd[rng.permutation(len(Xd))]
-    od = _oracle_index(Xd, 8, 40)
-    hd = Ohnsw.Hgraph(16, capi.L2, 8, 40, flavour=capi.FLAVOUR_HNSW_BA).import_graph(Xd, od.export())
-    od.set_accept_ties(True)
-    ids_o, d_o, cnt_o = od.search(Q, 10, 16, counters=True)
-    ids_g, d_g = Ohnsw.knn_batch_bigarray(hd, Q, k=10, ef=16)
-    assert_same_results(ids_g, d_g, ids_o, np.where(ids_o < 0, np.float32(np.inf), d_o))
-    assert np.array_equal(hd.last_search_counters(len(Q)).astype(np.uint64), cnt_o)
-    spills += hd.stats().search_tie_spills
-    assert hd.stats().search_tie_overflows == 0
-    assert spills > 0, "no query of this test outgrew the 32-entry shared tie list: the spill path is untested"
+    assert spills == 0          # duplicates are never linked to each other by the heuristic: few of them are visited
+
+
+def test_tie_list_beyond_shared_memory_is_exact():
+    """All 1 120 vectors of {-1,0,1}^8 with four non-zeros are at squared distance 4 from the origin, and at one
+    of three distances from (0.5, 0, ..., 0) — exact in fp32.  Closer candidates then evict beam entries that
+    tie with the new top one by one, and those stay poppable (strict stop rule, lib/ohnsw.ml:568): with
+    ef = 128 far more than the 32 the shared-memory tie list holds.  The list continues in a global region,
+    so ids, distances and work counters are still the oracle's, under both acceptance rules."""
+    import itertools
+    pts = []
+    for nz in itertools.combinations(range(8), 4):
+        for signs in itertools.product((-1.0, 1.0), repeat=4):
+            v = np.zeros(8, np.float32)
+            v[list(nz)] = signs
+            pts.append(v)
+    X = np.array(pts, np.float32)[np.random.default_rng(3).permutation(len(pts))]
+    Q = np.zeros((12, 8), np.float32)
+    Q[:, 0] = [0.5, -0.5, 0.25, 0.0, 0.5, 0.75, -0.25, 0.5, 0.0, 0.125, 0.5, -0.5]
+    Q[4:8, 1] = 0.5
+    Q[8:, 2] = [0.25, 0.5, -0.5, 0.125]
+    o = _oracle_index(X, 12, 60)
+    spills = 0
+    h = _gpu_from(o, X, 12, 60)
+    for k, ef in [(10, 128), (10, 64), (40, 200), (10, 10)]:
+        _check(o, h, Q, k, ef)
+        st = h.stats()
+        spills += st.search_tie_spills
+        assert st.search_tie_overflows == 0
+    assert spills > 0, "path B rule: no query outgrew the 32-entry shared tie list"
+    hb = Ohnsw.Hgraph(8, capi.L2, 12, 60, flavour=capi.FLAVOUR_HNSW_BA).import_graph(X, o.export())
+    o.set_accept_ties(True)
+    spills = 0
+    for k, ef in [(10, 16), (10, 128), (5, 40)]:
+        ids_o, d_o, cnt_o = o.search(Q, k, ef, counters=True)
+        ids_g, d_g = Ohnsw.knn_batch_bigarray(hb, Q, k=k, ef=ef)
+        assert_same_results(ids_g, d_g, ids_o, np.where(ids_o < 0, np.float32(np.inf), d_o))
+        assert np.array_equal(hb.last_search_counters(len(Q)).astype(np.uint64), cnt_o)
+        st = hb.stats()
+        spills += st.search_tie_spills
+        assert st.search_tie_overflows == 0
+    assert spills > 0, "accept-ties rule: no query outgrew the 32-entry shared tie list"
 
 
 def test_device_queries_with_padded_rows():
