@@ -72,16 +72,18 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
   int extra = pl.q_chunks * 16 + bp.sel_cap * 4 + stage_bytes;
-  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 32 * ef), 128);
+  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 8) : round_up(std::max(1024, 32 * ef), 128);
+  const int eb = hash_entry_bytes(x, hs, n_total);
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + extra;
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
-  hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
-  if (x->param_visited_mode != 1 && x->param_hash_slots == 0 && fixed + hs * 4 > 14 * 1024 &&
+  hs = std::min(hs, (x->max_smem_optin - fixed) / eb / 8 * 8);
+  if (x->param_visited_mode != 1 && x->param_hash_slots == 0 && fixed + hs * eb > 14 * 1024 &&
       (double)n_total / 8.0 <= 0.3 * 26.0 * ef * 4.0 * x->dim) hs = 0;      // see use_bitset_visited
   if (x->param_visited_mode == 2) hs = 0;
   pl.hash_slots = hs;
-  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, hs, pl.q_chunks, pl.nb_cap) + extra;
+  pl.hc = make_hash_cfg(x, hs, n_total);
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, (int)pl.hc.bytes, pl.q_chunks, pl.nb_cap) + extra;
   if (pl.smem_per_warp > x->max_smem_optin) fail(HNSWB200_EINVAL, "build: num_nodes_search_construction too large for shared memory");
   // pack the SM: as many warps as shared memory allows (<= 32), split into CTAs of <= 8 warps
   int per_sm_warps = std::max(1, std::min(32, (int)((size_t)(227 * 1024) / (size_t)(pl.smem_per_warp + 128))));
@@ -155,7 +157,7 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   sp.g = x->view();
   sp.queries = nullptr; sp.nq = B; sp.ef = x->efC; sp.k = x->efC; sp.ef_cap = pl.ef_cap;
   sp.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA; sp.pad_inf = 0;
-  sp.hash_slots = pl.hash_slots; sp.q_smem_chunks = pl.q_chunks; sp.smem_per_warp = pl.smem_per_warp; sp.nb_cap = pl.nb_cap;
+  sp.hc = pl.hc; sp.q_smem_chunks = pl.q_chunks; sp.smem_per_warp = pl.smem_per_warp; sp.nb_cap = pl.nb_cap;
   sp.stage_slots = pl.stage_slots; sp.stage_ahead = stage_ahead_for(x);
   sp.out_ids = nullptr; sp.out_dists = nullptr; sp.counters = nullptr; sp.next_query = nullptr;
   sp.bitset_pool = x->d_bitpool.p; sp.pool_busy = x->d_pool_busy.p; sp.pool_size = x->pool_size; sp.words = x->pool_words;

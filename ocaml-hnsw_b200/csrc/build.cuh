@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   w.newd = reinterpret_cast<float*>(w.newid + p.nb_cap);
   w.qs = reinterpret_cast<float4*>(w.newd + p.nb_cap);
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
-  float4* qs2 = reinterpret_cast<float4*>(w.vis.tab + p.hash_slots);
+  float4* qs2 = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(w.vis.tab) + p.hc.bytes);
   uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);
   stage_attach(w.st, reinterpret_cast<unsigned char*>(sel + bp.sel_cap), p.stage_slots, p.stage_ahead, g.ld4, lane);
   w.tie_spill = nullptr; w.tie_slot = -1;
@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     for (int layer = min(lv, g.max_layer); layer >= 0; layer--) {       // :806
       // search_k (:811): the beam is seeded with every element of w_queue, all unexpanded,
       // all marked visited (:555-557)
-      visited_clear(w.vis, lane);
-      for (int i = lane; i < n; i += 32) {
-        uint64_t k = w.keys[i] & ~1ull;
-        w.keys[i] = k;
-        visited_test_and_set(w.vis, key_id(k));
+      visited_clear(w.vis, p.hc, lane);
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        uint64_t k = 0;
+        if (i < n) { k = w.keys[i] & ~1ull; w.keys[i] = k; }
+        visited_test_and_set(w.vis, p, i < n, key_id(k), lane);
       }
       w.vis.count = n;
       __syncwarp();

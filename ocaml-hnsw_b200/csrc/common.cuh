@@ -325,29 +325,69 @@ __device__ __forceinline__ void batch_dist_staged(const GraphView& g, const floa
 }
 
 // ---- exact visited set ---------------------------------------------------------------------------
-// Open-addressing hash of id+1 in shared memory; when it would exceed its load bound the set
-// moves to a bitset over all n nodes borrowed from a global pool (exactness is never traded).
+// Open-addressing hash in shared memory; when it would exceed its load bound (or a probe sequence
+// its reach) the set moves to a bitset over all n nodes borrowed from a global pool — exactness is
+// never traded.  Two entry formats:
+//   32-bit  the id + 1, home slot by multiply-shift.
+//   16-bit  "quotiented": ids are first scrambled by a bijection of [0, 2^b) (odd multiplier, b = bits
+//           of n), id' = q * slots + home; the entry at displacement d from `home` stores
+//           1 + (q << db | d).  (home, q) determine id' and d determines home, so membership is
+//           exact with half the shared memory: q < 2^b / slots needs ~10 bits at 1M rows and 1 800
+//           slots, which leaves 6 bits of displacement; a probe that would need more spills.
+struct HashCfg {
+  uint32_t slots;      // entries (a multiple of 8); 0 = the set is a global bitset from the start
+  uint32_t bytes;      // table bytes, a multiple of 16
+  uint32_t bits16;     // entry format
+  uint32_t mask;       // 2^b - 1
+  uint32_t magic, shift;   // x / slots == __umulhi(x, magic) >> shift for every x <= mask (checked by the host)
+  uint32_t db;         // displacement bits
+  uint32_t mul, mul_inv;   // odd multiplier and its inverse mod 2^32
+};
 struct VisitedSet {
-  uint32_t* tab;        // shared, `slots` slots (a multiple of 4, not necessarily a power of two)
-  uint32_t slots;
+  uint32_t* tab;        // shared
   uint32_t limit;       // max entries kept in shared memory
   uint32_t count;       // warp-uniform
   uint32_t* bits;       // non-null once spilled
   int pool_slot;
 };
-__device__ __forceinline__ bool hash_test_and_set(uint32_t* tab, uint32_t slots, uint32_t id) {
-  uint32_t key = id + 1u;
-  uint32_t h = __umulhi(id * 2654435761u, slots);          // multiply-shift range reduction
-  while (true) {
-    uint32_t old = atomicCAS(&tab[h], 0u, key);
-    if (old == 0u) return true;
-    if (old == key) return false;
-    h = h + 1u == slots ? 0u : h + 1u;
+// 1 = newly added, 0 = was present, 2 = could not be placed (16-bit format: displacement out of reach)
+__device__ __forceinline__ int hash_test_and_set(uint32_t* tab, const HashCfg& hc, uint32_t id) {
+  if (!hc.bits16) {
+    const uint32_t key = id + 1u;
+    uint32_t h = __umulhi(id * 2654435761u, hc.slots);          // multiply-shift range reduction
+    while (true) {
+      const uint32_t old = atomicCAS(&tab[h], 0u, key);
+      if (old == 0u) return 1;
+      if (old == key) return 0;
+      h = h + 1u == hc.slots ? 0u : h + 1u;
+    }
   }
+  unsigned short* t16 = reinterpret_cast<unsigned short*>(tab);
+  const uint32_t x = (id * hc.mul) & hc.mask;
+  const uint32_t q = __umulhi(x, hc.magic) >> hc.shift;
+  uint32_t h = x - q * hc.slots;
+  const uint32_t dmax = 1u << hc.db;
+  for (uint32_t d = 0; d < dmax; d++) {
+    const unsigned short want = (unsigned short)(1u + ((q << hc.db) | d));
+    const unsigned short old = atomicCAS(&t16[h], (unsigned short)0, want);
+    if (old == 0) return 1;
+    if (old == want) return 0;
+    h = h + 1u == hc.slots ? 0u : h + 1u;
+  }
+  return 2;
 }
-__device__ __forceinline__ void visited_clear(VisitedSet& v, int lane) {
+// the id stored in slot `s` (0xffffffff if the slot is empty): used when the set moves to the bitset
+__device__ __forceinline__ uint32_t hash_decode(const uint32_t* tab, const HashCfg& hc, uint32_t s) {
+  if (!hc.bits16) { const uint32_t key = tab[s]; return key ? key - 1u : 0xffffffffu; }
+  const uint32_t e = reinterpret_cast<const unsigned short*>(tab)[s];
+  if (!e) return 0xffffffffu;
+  const uint32_t v = e - 1u, d = v & ((1u << hc.db) - 1u), q = v >> hc.db;
+  const uint32_t home = s >= d ? s - d : s + hc.slots - d;
+  return ((q * hc.slots + home) * hc.mul_inv) & hc.mask;
+}
+__device__ __forceinline__ void visited_clear(VisitedSet& v, const HashCfg& hc, int lane) {
   uint4* t4 = reinterpret_cast<uint4*>(v.tab);
-  for (uint32_t i = lane; i < v.slots / 4u; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = lane; i < hc.bytes / 16u; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
   v.count = 0;
   __syncwarp();
 }

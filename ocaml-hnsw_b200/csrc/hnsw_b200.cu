@@ -97,6 +97,7 @@ struct hnswb200_index {
   int64_t param_host_chunks = 0;
   int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
   int64_t param_stage_ahead = -1;       // rows beyond the ring prefetched to L2 (-1 auto, 0..31)
+  int64_t param_hash_bits = 0;          // visited hash entries: 0 auto (16-bit quotiented when the id range allows), 16, 32
   unsigned int* h_ready = nullptr;      // pinned: the "pieces ready" values the copy stream writes after each piece
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_q, d_dists;
@@ -170,6 +171,7 @@ void upload_rows(float* dst, int ld, const float* src, int dim, int64_t n, cudaS
 // ---- search ---------------------------------------------------------------------------------------
 struct SearchPlan {
   int cpl, warps, ef_cap, hash_slots, q_chunks, smem_per_warp, grid, nb_cap;
+  hb::HashCfg hc;        // visited hash geometry for hash_slots entries
   int stage_slots;      // bulk-copy ring of this many rows per warp (0: LDG gathers)
   size_t smem;
 };
@@ -199,6 +201,56 @@ int search_resident(int cpl, int threads, size_t smem) {
   cache[key] = std::max(1, nb);
   return std::max(1, nb);
 }
+
+// Geometry of a visited hash of `slots` entries over ids < n (common.cuh, HashCfg).  16-bit quotiented
+// entries when the quotient leaves at least 5 bits of displacement and the division-by-multiplication
+// is exact on the whole id range (verified here); 32-bit entries otherwise.
+hb::HashCfg make_hash_cfg_uncached(const hnswb200_index* x, int slots, int64_t n) {
+  hb::HashCfg hc{};
+  hc.slots = (uint32_t)slots;
+  hc.bytes = (uint32_t)slots * 4u;
+  hc.mul = 2654435761u;
+  hc.mul_inv = 1u;
+  for (int i = 0; i < 5; i++) hc.mul_inv *= 2u - hc.mul * hc.mul_inv;      // Newton: inverse of an odd number mod 2^32
+  if (slots <= 0 || x->param_hash_bits == 32) return hc;
+  int b = 1;
+  while (b < 31 && (int64_t(1) << b) < std::max<int64_t>(n, 2)) b++;
+  const uint32_t mask = (uint32_t)((uint64_t(1) << b) - 1);
+  const uint32_t qmax = mask / (uint32_t)slots;
+  int db = 0;
+  while (db < 12 && ((((uint64_t)qmax << (db + 1)) | ((1u << (db + 1)) - 1u)) <= 65534u)) db++;
+  if (x->param_hash_bits < 0) db = std::min(db, (int)-x->param_hash_bits);      // tests: a short reach, so probes do run out
+  else if (db < 5 && x->param_hash_bits != 16) return hc;
+  if (db < 1) return hc;
+  // x / slots for x <= mask: magic = ceil(2^(32+shift) / slots) when it fits 32 bits, checked at every multiple of slots
+  int shift = 0;
+  while ((uint64_t(1) << shift) < (uint64_t)slots) shift++;
+  uint64_t magic = 0;
+  for (; shift >= 0; shift--) {
+    magic = ((uint64_t(1) << (32 + shift)) + (uint64_t)slots - 1) / (uint64_t)slots;
+    if (magic <= 0xffffffffull) break;
+  }
+  if (shift < 0) return hc;
+  auto div = [&](uint32_t v) { return (uint32_t)(((uint64_t)v * magic) >> 32) >> shift; };
+  for (uint64_t m = 0; m <= mask; m += (uint64_t)slots) {
+    if (div((uint32_t)m) != m / slots) return hc;
+    if (m && div((uint32_t)(m - 1)) != (m - 1) / slots) return hc;
+  }
+  if (div(mask) != mask / (uint32_t)slots) return hc;
+  hc.bits16 = 1; hc.bytes = (uint32_t)slots * 2u; hc.mask = mask; hc.magic = (uint32_t)magic; hc.shift = (uint32_t)shift; hc.db = (uint32_t)db;
+  return hc;
+}
+hb::HashCfg make_hash_cfg(const hnswb200_index* x, int slots, int64_t n) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int64_t, int64_t>, hb::HashCfg> cache;      // the exactness check below walks the id range
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_tuple(slots, n, x->param_hash_bits);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  return cache[key] = make_hash_cfg_uncached(x, slots, n);
+}
+int hash_entry_bytes(const hnswb200_index* x, int slots, int64_t n) { return make_hash_cfg(x, slots, n).bits16 ? 2 : 4; }
+
 
 // Visited set of a query: exact open-addressing hash in shared memory, or one n-bit set per warp
 // in global memory.  The hash costs shared memory (fewer resident warps: throughput is linear in
@@ -236,23 +288,25 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   pl.ef_cap = round_up(ef, 32);
   // visited hash: ~42 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
-  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 4) : round_up(std::max(1024, 42 * ef), 128);
+  int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 8) : round_up(std::max(1024, 42 * ef), 128);
+  const int eb = hash_entry_bytes(x, hs, x->n);                  // 2 (16-bit quotiented entries) or 4
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes;
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
-  hs = std::min(hs, (x->max_smem_optin - fixed) / 4 / 4 * 4);
+  hs = std::min(hs, (x->max_smem_optin - fixed) / eb / 8 * 8);
   {
     // a table within ~12 % of what keeps the SM full is trimmed to fit (the few queries that
     // outgrow it continue on a global bitset)
     const int budget = (227 * 1024) / (4 * HB_SEARCH_MINB) - 256;
-    const int hs_fit = (budget - fixed) / 4 / 4 * 4;
+    const int hs_fit = (budget - fixed) / eb / 8 * 8;
     if (x->param_hash_slots == 0 && hs > hs_fit && hs_fit * 100 >= hs * 88) hs = hs_fit;
   }
-  if (use_bitset_visited(x, ef, fixed + hs * 4, x->n)) hs = 0;
+  if (use_bitset_visited(x, ef, fixed + hs * eb, x->n)) hs = 0;
   pl.hash_slots = hs;
-  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, pl.hash_slots, pl.q_chunks, pl.nb_cap) + stage_bytes;
+  pl.hc = make_hash_cfg(x, hs, x->n);
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, (int)pl.hc.bytes, pl.q_chunks, pl.nb_cap) + stage_bytes;
   // A batch small enough to be resident all at once (one warp per query, nq <= SMs x warps per SM) gets the
   // deepest ring with which it still is: every query then runs from the first cycle, in CTAs of one warp so
   // the SMs hold the same number of queries (1 000 GIST queries: 7 per SM with a 6-row ring).
@@ -353,7 +407,7 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   p.queries = d_queries; p.nq = nq; p.ef = ef; p.k = k; p.ef_cap = pl.ef_cap;
   p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
   p.pad_inf = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
-  p.hash_slots = pl.hash_slots; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp; p.nb_cap = pl.nb_cap;
+  p.hc = pl.hc; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp; p.nb_cap = pl.nb_cap;
   p.stage_slots = pl.stage_slots;
   p.stage_ahead = stage_ahead_for(x);
   p.out_ids = d_ids; p.out_dists = d_dists; p.counters = counters;
@@ -367,7 +421,8 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   static const bool trace = std::getenv("HNSWB200_TRACE") != nullptr;
   if (trace)
     fprintf(stderr, "[hnsw_b200 search] nq=%lld ef=%d cpl=%d grid=%d x %d warps, %d B smem/warp (hash %d slots, ring %d rows), visited %s\n",
-            (long long)nq, ef, pl.cpl, q.grid, pl.warps, pl.smem_per_warp, pl.hash_slots, pl.stage_slots, pl.hash_slots ? "hash" : "bitset");
+            (long long)nq, ef, pl.cpl, q.grid, pl.warps, pl.smem_per_warp, pl.hash_slots, pl.stage_slots,
+            pl.hash_slots ? (pl.hc.bits16 ? "hash16" : "hash32") : "bitset");
   switch (pl.cpl) {
     case 1: launch_search<1>(p, q, s); break;
     case 2: launch_search<2>(p, q, s); break;
@@ -632,6 +687,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "host_chunks") x->param_host_chunks = value;
     else if (s == "stage_rows") x->param_stage_rows = value;
     else if (s == "stage_ahead") x->param_stage_ahead = value;
+    else if (s == "hash_bits") x->param_hash_bits = value;
     else if (s == "row_floats") {             // vector row stride in floats (multiple of 4, >= dim); only on an empty index
       if (x->n != 0) fail(HNSWB200_EINVAL, "row_floats can only be set on an empty index");
       if (value < x->dim || value % 4 != 0) fail(HNSWB200_EINVAL, "row_floats must be a multiple of 4 and >= dim");

@@ -34,7 +34,7 @@ struct SearchParams {
   int ef, k, ef_cap;
   int accept_ties;           // Hnsw.Ba flavour: accept d <= top (lib/hnsw.ml:494-506)
   int pad_inf;               // Hnsw.Ba flavour: +inf padding (lib/hnsw.ml:771)
-  int hash_slots;            // multiple of 4
+  HashCfg hc;                // visited hash geometry (hc.slots == 0: global bitset per warp)
   int nb_cap;                // list slots gathered per pass: 32 or 64 (staging arrays hold this many)
   int q_smem_chunks;         // float4 slots reserved for the query copy
   int stage_slots;           // > 0: rows are staged through a per-warp bulk-copy ring of this many rows (common.cuh)
@@ -65,8 +65,8 @@ struct SearchParams {
   unsigned int ready_step;
 };
 
-__host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_slots, int q_chunks, int nb_cap = 32) {
-  return ef_cap * 8 + TIES_CAP * 8 + nb_cap * 4 + nb_cap * 4 + q_chunks * 16 + hash_slots * 4;
+__host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_bytes, int q_chunks, int nb_cap = 32) {
+  return ef_cap * 8 + TIES_CAP * 8 + nb_cap * 4 + nb_cap * 4 + q_chunks * 16 + hash_bytes;
 }
 // the bulk-copy ring (when used) follows the fixed part of the warp's block
 __device__ __forceinline__ void stage_attach(Stage& st, unsigned char* at, int slots, int ahead, int ld4, int lane) {
@@ -105,9 +105,9 @@ __device__ __forceinline__ void visited_spill(VisitedSet& v, const SearchParams&
   s = __shfl_sync(FULL, s, 0);
   v.pool_slot = s;
   v.bits = p.bitset_pool + (size_t)s * p.words;
-  for (uint32_t i = lane; i < v.slots; i += 32) {
-    uint32_t key = v.tab[i];
-    if (key) { uint32_t id = key - 1u; atomicOr(&v.bits[id >> 5], 1u << (id & 31)); }
+  for (uint32_t i = lane; i < p.hc.slots; i += 32) {
+    const uint32_t id = hash_decode(v.tab, p.hc, i);
+    if (id != 0xffffffffu) atomicOr(&v.bits[id >> 5], 1u << (id & 31));
   }
   __syncwarp();
 }
@@ -116,7 +116,7 @@ __device__ __forceinline__ void visited_release(VisitedSet& v, const SearchParam
     uint4* b4 = reinterpret_cast<uint4*>(v.bits);
     for (int i = lane; i < p.words / 4; i += 32) b4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    if (v.slots == 0u) return;                 // bitset is this warp's primary set: it keeps its slot
+    if (p.hc.slots == 0u) return;              // bitset is this warp's primary set: it keeps its slot
     __threadfence();
     if (lane == 0) atomicExch(&p.pool_busy[v.pool_slot], 0);
     v.bits = nullptr;
@@ -126,23 +126,29 @@ __device__ __forceinline__ void visited_release(VisitedSet& v, const SearchParam
 // shared memory, so every warp owns one n-bit set of the global pool for its whole life.
 __device__ __forceinline__ void visited_init(VisitedSet& v, const SearchParams& p, uint32_t* tab) {
   v.tab = tab;
-  v.slots = (uint32_t)p.hash_slots;
-  v.limit = (uint32_t)p.hash_slots / 4u * 3u;                                // load <= 0.75
+  v.limit = p.hc.slots / 4u * 3u;                                             // load <= 0.75
   v.bits = nullptr;
   v.pool_slot = -1;
-  if (p.hash_slots == 0) {
+  if (p.hc.slots == 0) {
     v.pool_slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);        // host guarantees pool_size >= warps
     v.bits = p.bitset_pool + (size_t)v.pool_slot * p.words;
     v.limit = 0xffffffffu;
   }
 }
-// true if `id` was not yet visited (and marks it).  Called by a subset of lanes.
-__device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id) {
-  if (v.bits) {
-    uint32_t bit = 1u << (id & 31);
-    return !(atomicOr(&v.bits[id >> 5], bit) & bit);
-  }
-  return hash_test_and_set(v.tab, v.slots, id);
+__device__ __forceinline__ bool bitset_test_and_set(uint32_t* bits, uint32_t id) {
+  const uint32_t bit = 1u << (id & 31);
+  return !(atomicOr(&bits[id >> 5], bit) & bit);
+}
+// Visited.mem / Visited.add for up to one id per lane (`active` lanes): true where the id was not yet
+// visited (and marks it).  All 32 lanes must call.  A lane whose id cannot be placed in the 16-bit
+// table makes the whole set move to the global bitset, where it is then placed.
+__device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, const SearchParams& p, bool active, uint32_t id, int lane) {
+  if (v.bits) return active && bitset_test_and_set(v.bits, id);
+  const int r = active ? hash_test_and_set(v.tab, p.hc, id) : 0;
+  if (!p.hc.bits16 || !__any_sync(FULL, r == 2)) return r == 1;
+  __syncwarp();
+  visited_spill(v, p, lane);
+  return r == 2 ? bitset_test_and_set(v.bits, id) : r == 1;
 }
 
 // ---- the tie list: evicted candidates whose distance equals the beam's top ------------------------
@@ -259,7 +265,7 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
         unsigned valid = __ballot_sync(FULL, nb >= 0);
         if (!valid) { row_ended = true; break; }
         if (!w.vis.bits && w.vis.count + 32u > w.vis.limit) visited_spill(w.vis, p, lane);
-        bool is_new = nb >= 0 && visited_test_and_set(w.vis, (uint32_t)nb);   // Visited.mem / add (:571-572)
+        const bool is_new = visited_test_and_set(w.vis, p, nb >= 0, (uint32_t)nb, lane);   // Visited.mem / add (:571-572)
         unsigned m = __ballot_sync(FULL, is_new);
         if (is_new) w.newid[total + __popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
         total += __popc(m);
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
   w.newd = reinterpret_cast<float*>(w.newid + p.nb_cap);
   w.qs = reinterpret_cast<float4*>(w.newd + p.nb_cap);
   visited_init(w.vis, p, reinterpret_cast<uint32_t*>(w.qs + p.q_smem_chunks));
-  stage_attach(w.st, reinterpret_cast<unsigned char*>(w.vis.tab + p.hash_slots), p.stage_slots, p.stage_ahead, g.ld4, lane);
+  stage_attach(w.st, reinterpret_cast<unsigned char*>(w.vis.tab) + p.hc.bytes, p.stage_slots, p.stage_ahead, g.ld4, lane);
   w.tie_spill = nullptr; w.tie_slot = -1;
 
   while (true) {
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     // target -> registers (or shared for the generic path)
     if (HB_SEARCH_QREG) load_target<CPL>(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.q, w.qs, lane);
     else load_target_smem(g, reinterpret_cast<const float4*>(p.queries) + (size_t)qi * g.ld4, w.qs, p.q_smem_chunks, lane);
-    visited_clear(w.vis, lane);
+    visited_clear(w.vis, p.hc, lane);
 
     uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
     bool tie_overflow = false;
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     n_dist++;                                       // MinQueue.add_node w_queue !node
     if (lane == 0) w.keys[0] = make_key(d_cur, cur);
     int n = 1;
-    visited_test_and_set(w.vis, lane == 0 ? cur : cur);   // all lanes race on the same slot: one wins
+    visited_test_and_set(w.vis, p, lane == 0, cur, lane);
     w.vis.count = 1;
     __syncwarp();
     layer_search(p, w, 0, n, n_dist, n_exp0, tie_overflow);

@@ -365,3 +365,21 @@ def test_staged_gather_equals_ldg_gather(dim, M):
     base = rows[(-1, 1)]
     for key, r in rows.items():
         assert_same_results(r[0], r[1], base[0], base[1])
+
+
+@pytest.mark.parametrize("hash_bits", [32, 16, -2])
+def test_visited_hash_formats_are_exact(uni2k, hash_bits):
+    """The shared-memory visited hash holds 32-bit ids or 16-bit quotiented entries (quotient + displacement,
+    half the memory); -2 caps the displacement at 3 slots so that probe sequences do run out and the set
+    moves to the global bitset mid-expansion.  Every variant must give the oracle's rows and counters."""
+    X, Q, o, _ = uni2k
+    h = _gpu_from(o, X, 16, 100)
+    h.set_param("visited_mode", 1)
+    h.set_param("hash_bits", hash_bits)
+    for k, ef in [(10, 10), (10, 64), (10, 200)]:
+        _check(o, h, Q, k, ef)
+    if hash_bits == -2:
+        assert h.stats().search_visited_overflows > 0
+    h.set_param("hash_slots", 1024)                      # and with a table every query outgrows
+    _check(o, h, Q, 10, 200)
+    assert h.stats().search_visited_overflows > 0
