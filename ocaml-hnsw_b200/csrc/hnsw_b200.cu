@@ -289,12 +289,16 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   // visited hash: ~42 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 8) : round_up(std::max(1024, 42 * ef), 128);
-  const int eb = hash_entry_bytes(x, hs, x->n);                  // 2 (16-bit quotiented entries) or 4
+  int eb = hash_entry_bytes(x, hs, x->n);                        // 2 (16-bit quotiented entries) or 4
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes;
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
+  // 16-bit entries cost a few more instructions per test-and-set: only where 32-bit ones would leave
+  // fewer warps resident than the register file allows (ef >~ 42 at 128 dimensions)
+  bool force32 = false;
+  if (eb == 2 && x->param_hash_bits == 0 && (227 * 1024) / (fixed + hs * 4 + 256) >= 4 * HB_SEARCH_MINB) { eb = 4; force32 = true; }
   hs = std::min(hs, (x->max_smem_optin - fixed) / eb / 8 * 8);
   {
     // a table within ~12 % of what keeps the SM full is trimmed to fit (the few queries that
@@ -306,6 +310,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   if (use_bitset_visited(x, ef, fixed + hs * eb, x->n)) hs = 0;
   pl.hash_slots = hs;
   pl.hc = make_hash_cfg(x, hs, x->n);
+  if (force32 && pl.hc.bits16) { pl.hc.bits16 = 0; pl.hc.bytes = (uint32_t)hs * 4u; }
   pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, (int)pl.hc.bytes, pl.q_chunks, pl.nb_cap) + stage_bytes;
   // A batch small enough to be resident all at once (one warp per query, nq <= SMs x warps per SM) gets the
   // deepest ring with which it still is: every query then runs from the first cycle, in CTAs of one warp so

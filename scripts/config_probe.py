@@ -82,7 +82,7 @@ def run(reps=5):
     return min(ms), float(np.mean(ms)), s
 
 
-known = ("stage_rows", "max_warps_per_sm", "visited_mode", "hash_slots", "warps_per_cta")
+known = ("stage_rows", "max_warps_per_sm", "visited_mode", "hash_slots", "warps_per_cta", "hash_bits")
 defaults = {"stage_ahead": -1}
 for setting in [{}] + settings:
     for name in known + tuple(defaults):

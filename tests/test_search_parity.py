@@ -367,19 +367,23 @@ def test_staged_gather_equals_ldg_gather(dim, M):
         assert_same_results(r[0], r[1], base[0], base[1])
 
 
-@pytest.mark.parametrize("hash_bits", [32, 16, -2])
+@pytest.mark.parametrize("hash_bits", [32, 16, -1])
 def test_visited_hash_formats_are_exact(uni2k, hash_bits):
     """The shared-memory visited hash holds 32-bit ids or 16-bit quotiented entries (quotient + displacement,
-    half the memory); -2 caps the displacement at 3 slots so that probe sequences do run out and the set
+    half the memory); -1 caps the displacement at one slot so that probe sequences do run out and the set
     moves to the global bitset mid-expansion.  Every variant must give the oracle's rows and counters."""
     X, Q, o, _ = uni2k
     h = _gpu_from(o, X, 16, 100)
     h.set_param("visited_mode", 1)
     h.set_param("hash_bits", hash_bits)
+    if hash_bits == -1:
+        h.set_param("hash_slots", 1024)                  # 2 000 ids over 1 024 slots: neighbours in the table do collide
+        _check(o, h, Q, 10, 10)                          # ~400 visited nodes: far below the load bound of 768
+        assert h.stats().search_visited_overflows > 0    # so every spill here is a probe that ran out of reach
+        _check(o, h, Q, 10, 64)
+        return
     for k, ef in [(10, 10), (10, 64), (10, 200)]:
         _check(o, h, Q, k, ef)
-    if hash_bits == -2:
-        assert h.stats().search_visited_overflows > 0
     h.set_param("hash_slots", 1024)                      # and with a table every query outgrows
     _check(o, h, Q, 10, 200)
     assert h.stats().search_visited_overflows > 0
