@@ -5,7 +5,11 @@
  *
  *   gcc -O2 -Iinclude examples/benchmark_c.c -Locaml-hnsw_b200 -lhnsw_b200 \
  *       -Wl,-rpath,$PWD/ocaml-hnsw_b200 -lm -o build/benchmark_c
- *   build/benchmark_c [n] [dim] [nq] [M] [efC] [k] [ef]
+ *   build/benchmark_c [--gpus N | --shards S] [n] [dim] [nq] [M] [efC] [k] [ef]
+ *
+ * --gpus N cuts the rows into N shards, one per GPU (hnswb200_sharded_*: one process drives every GPU,
+ * per-shard rows exchanged by peer stores and merged inside the search kernel); --shards S places S
+ * shards on device 0 (the same kernels on a one-GPU box).
  *
  * Exit status: 0 on success, 3 when the library reports an error (e.g. no CUDA device: there is
  * no CPU fallback), 4 when recall is below 0.9. */
@@ -13,6 +17,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 #include "hnsw_b200.h"
 
@@ -39,6 +44,12 @@ static double now(void) {
 }
 
 int main(int argc, char** argv) {
+  int shards = 0, spread = 0;                          /* 0: a single hnswb200_index */
+  if (argc > 2 && (!strcmp(argv[1], "--gpus") || !strcmp(argv[1], "--shards"))) {
+    spread = !strcmp(argv[1], "--gpus");
+    shards = atoi(argv[2]);
+    argv += 2; argc -= 2;
+  }
   int64_t n = argc > 1 ? atoll(argv[1]) : 10000;       /* benchmark.ml's default shape: 10k x 128 */
   int dim = argc > 2 ? atoi(argv[2]) : 128;
   int64_t nq = argc > 3 ? atoll(argv[3]) : 10;         /* benchmark.ml queries 10 points */
@@ -65,25 +76,47 @@ int main(int argc, char** argv) {
 
   printf("%s\n", hnswb200_version());
   hnswb200_index* h = NULL;
-  CHECK(hnswb200_create(&h, dim, HNSWB200_L2, M, efc, /*seed*/ 0, /*device*/ 0));
-  double t0 = now();
-  CHECK(hnswb200_build(h, train, n, NULL));              /* Ohnsw.build_batch_bigarray, benchmark.ml:76 */
-  double t_build = now() - t0;
-
+  hnswb200_sharded* sh = NULL;
   int32_t* ids = malloc(sizeof(int32_t) * nq * k);
   float* dists = malloc(sizeof(float) * nq * k);
   float* exact = malloc(sizeof(float) * nq * k);
-  t0 = now();
-  CHECK(hnswb200_search(h, test, nq, k, ef, HNSWB200_MODE_PARITY, ids, dists));   /* knn_batch_bigarray, :91 */
-  double t_search = now() - t0;
+  double t0, t_build, t_search;
+  if (shards > 0) {
+    int devices[32];
+    if (shards > 32) shards = 32;
+    for (int i = 0; i < shards; ++i) devices[i] = spread ? i : 0;
+    CHECK(hnswb200_sharded_create(&sh, dim, HNSWB200_L2, M, efc, /*seed*/ 0, shards, devices));
+    t0 = now();
+    CHECK(hnswb200_sharded_build(sh, train, n, NULL));
+    t_build = now() - t0;
+    CHECK(hnswb200_sharded_search(sh, test, nq, k, ef, HNSWB200_MODE_PARITY, ids, dists));   /* warm-up: buffers, peer mappings */
+    t0 = now();
+    CHECK(hnswb200_sharded_search(sh, test, nq, k, ef, HNSWB200_MODE_PARITY, ids, dists));
+    t_search = now() - t0;
+  } else {
+    CHECK(hnswb200_create(&h, dim, HNSWB200_L2, M, efc, /*seed*/ 0, /*device*/ 0));
+    t0 = now();
+    CHECK(hnswb200_build(h, train, n, NULL));              /* Ohnsw.build_batch_bigarray, benchmark.ml:76 */
+    t_build = now() - t0;
+    t0 = now();
+    CHECK(hnswb200_search(h, test, nq, k, ef, HNSWB200_MODE_PARITY, ids, dists));   /* knn_batch_bigarray, :91 */
+    t_search = now() - t0;
+  }
   CHECK(hnswb200_bruteforce_knn(train, n, test, nq, dim, k, HNSWB200_L2, 0, NULL, exact));   /* dataset.ml:15 */
   double recall = 0;
   CHECK(hnswb200_recall(exact, dists, nq, k, 1e-8, &recall));                     /* dataset.ml:105 */
 
   hnswb200_info inf;
   hnswb200_stats st;
-  CHECK(hnswb200_get_info(h, &inf));
-  CHECK(hnswb200_get_stats(h, &st));
+  if (sh) {
+    int ns = 0;
+    CHECK(hnswb200_sharded_get_info(sh, &inf, &ns));
+    CHECK(hnswb200_sharded_get_stats(sh, &st));
+    printf("%d shards on %s\n", ns, spread ? "one GPU each" : "device 0");
+  } else {
+    CHECK(hnswb200_get_info(h, &inf));
+    CHECK(hnswb200_get_stats(h, &st));
+  }
   printf("n=%lld dim=%d M=%d efC=%d: build %.3f s, max_layer %d, entry %lld\n", (long long)inf.n, inf.dim, inf.M,
          inf.ef_construction, t_build, inf.max_layer, (long long)inf.entry_point);
   printf("nq=%lld k=%d ef=%d: search %.3f ms (kernel %.3f ms), %.1f distance evaluations per query\n", (long long)nq, k, ef,
@@ -91,7 +124,8 @@ int main(int argc, char** argv) {
   printf("first query: ");
   for (int i = 0; i < k; ++i) printf("%d:%.4f ", ids[i], dists[i]);
   printf("\nrecall %.4f\n", recall);
-  CHECK(hnswb200_destroy(h));
+  if (sh) CHECK(hnswb200_sharded_destroy(sh));
+  else CHECK(hnswb200_destroy(h));
   free(basis); free(train); free(test); free(ids); free(dists); free(exact);
   return recall >= 0.9 ? 0 : 4;
 }

@@ -216,6 +216,53 @@ int hnswb200_merge_topk_device(const int32_t* d_ids, const float* d_dists, int n
                                int k, int64_t shard_stride, const int64_t* shard_offsets,
                                int32_t* d_out_ids, float* d_out_dists, void* stream);
 
+/* ---- multi-GPU inside the library: one process drives every GPU --------------- */
+
+/* The reference builds / queries everything with ONE call (lib/ohnsw.ml:840-841, :877); a host that is
+ * not a torchrun job (the OCaml benchmark, examples/benchmark_c.c) reaches N GPUs through this handle.
+ * The dataset is cut into `n_shards` contiguous row ranges [i*n/S, (i+1)*n/S); shard i lives on CUDA
+ * device devices[i] (NULL = 0, 1, 2, ...; a device may be named more than once) and is an ordinary
+ * hnswb200_index.  No torch, no NCCL: a search copies the queries to the first shard's device once and
+ * from there GPU to GPU, every shard's kernel stores its finished rows (ids already global) straight
+ * into a gather block on that device through the NVLink peer mapping, and the last warp to arrive
+ * for a query merges its rows in place — no all-gather, no barrier kernel, no merge launch. */
+typedef struct hnswb200_sharded hnswb200_sharded;
+int hnswb200_sharded_create(hnswb200_sharded** out, int dim, int metric, int M, int ef_construction,
+                            uint64_t seed, int n_shards, const int* devices);
+int hnswb200_sharded_destroy(hnswb200_sharded* s);
+/* hnswb200_set_param / hnswb200_set_flavour on every shard; plus "query_path" (0: one H2D copy then GPU-to-GPU
+ * copies, the default; 1: one H2D copy per device). */
+int hnswb200_sharded_set_param(hnswb200_sharded* s, const char* name, int64_t value);
+int hnswb200_sharded_set_flavour(hnswb200_sharded* s, int flavour);
+/* Ohnsw.build_batch_bigarray (lib/ohnsw.ml:840-857) over all shards at once, one host thread per shard.
+ * `levels` (int32[n], may be NULL) as in hnswb200_build. */
+int hnswb200_sharded_build(hnswb200_sharded* s, const float* data, int64_t n, const int32_t* levels);
+/* Ohnsw.knn_batch_bigarray (lib/ohnsw.ml:877-897): host buffers, global ids, rows ascending by
+ * (distance, id) over all shards, -1 / NaN padded. */
+int hnswb200_sharded_search(hnswb200_sharded* s, const float* queries, int64_t nq, int k, int ef, int mode,
+                            int32_t* ids, float* dists);
+/* Same with every buffer on the FIRST shard's device (queries dense [nq][dim]); `stream` as in
+ * hnswb200_search_device (a stream of that device; NULL = synchronous). */
+int hnswb200_sharded_search_device(hnswb200_sharded* s, const float* d_queries, int64_t nq, int k, int ef, int mode,
+                                   int32_t* d_ids, float* d_dists, void* stream);
+/* Shard i as a plain index (import / export / stats / per-query counters) and its first global row. */
+int hnswb200_sharded_shard(hnswb200_sharded* s, int i, hnswb200_index** out, int64_t* first_row);
+/* n = total rows; max_layer = the highest over the shards; entry_point = -1 (per shard). */
+int hnswb200_sharded_get_info(hnswb200_sharded* s, hnswb200_info* out, int* n_shards);
+/* Counters summed over the shards; search_kernel_ms = device time of the last search step (first query
+ * copy to the last shard's kernel end, merge included); build_seconds = the slowest shard's. */
+int hnswb200_sharded_get_stats(hnswb200_sharded* s, hnswb200_stats* out);
+
+/* One process per GPU (torchrun) with caller-provided peer-mapped buffers (torch symmetric memory): shard
+ * `shard` of `n_shards` searches its own index `idx` and takes part in the same fused exchange + merge.
+ * g_ids / g_dists ([n_shards][nq][k]) and arrive (uint32[nq], zero before the call) live on one home rank
+ * and are mapped on every rank; the merged rows are stored into each of the n_final (1..8) destinations.
+ * The caller separates consecutive calls that reuse `arrive` with a barrier. */
+int hnswb200_search_device_sharded(hnswb200_index* idx, const float* d_queries, int64_t nq, int k, int ef, int mode,
+                                   int shard, int n_shards, int64_t first_row, int32_t* g_ids, float* g_dists,
+                                   uint32_t* arrive, int n_final, int32_t* const* f_ids, float* const* f_dists,
+                                   void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 
 int hnswb200_get_info(hnswb200_index* idx, hnswb200_info* out);

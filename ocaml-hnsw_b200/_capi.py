@@ -62,6 +62,17 @@ SIGNATURES = {
     "hnswb200_bruteforce_last_unproven": (_i64, []),
     "hnswb200_recall": (_i32, [_vp, _vp, _i64, _i32, _f64, C.POINTER(_f64)]),
     "hnswb200_merge_topk_device": (_i32, [_vp, _vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "hnswb200_sharded_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i32, _i32, _u64, _i32, _vp]),
+    "hnswb200_sharded_destroy": (_i32, [_vp]),
+    "hnswb200_sharded_set_param": (_i32, [_vp, C.c_char_p, _i64]),
+    "hnswb200_sharded_set_flavour": (_i32, [_vp, _i32]),
+    "hnswb200_sharded_build": (_i32, [_vp, _vp, _i64, _vp]),
+    "hnswb200_sharded_search": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "hnswb200_sharded_search_device": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hnswb200_sharded_shard": (_i32, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64)]),
+    "hnswb200_sharded_get_info": (_i32, [_vp, C.POINTER(Info), C.POINTER(_i32)]),
+    "hnswb200_sharded_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
+    "hnswb200_search_device_sharded": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "hnswb200_get_info": (_i32, [_vp, C.POINTER(Info)]),
     "hnswb200_get_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "hnswb200_host_register": (_i32, [_vp, _i64]),

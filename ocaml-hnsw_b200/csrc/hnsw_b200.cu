@@ -405,9 +405,10 @@ void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
 void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_queries, int64_t nq, int k, int ef,
                     int32_t* d_ids, float* d_dists, uint32_t* counters, unsigned int* next, cudaStream_t s,
                     int n_peer = 0, int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr,
-                    const unsigned int* ready = nullptr, unsigned int ready_step = 1) {
+                    const unsigned int* ready = nullptr, unsigned int ready_step = 1, const hb::ShardTail* tail = nullptr) {
   hb::SearchParams p;
   p.ready = ready; p.ready_step = ready_step;
+  if (tail) p.tail = *tail; else p.tail.n_shards = 0;
   p.g = x->view();
   p.queries = d_queries; p.nq = nq; p.ef = ef; p.k = k; p.ef_cap = pl.ef_cap;
   p.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA;
@@ -452,7 +453,7 @@ void finish_search(hnswb200_index* x, const unsigned long long* evs, int mode) {
 
 void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode,
                    int32_t* d_ids, float* d_dists, cudaStream_t s, bool own_stream, int n_peer = 0,
-                   int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr) {
+                   int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr, const hb::ShardTail* tail = nullptr) {
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
   SearchPlan pl = plan_search(x, ef, nq);
@@ -467,7 +468,8 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, sizeof(unsigned int), s));
   CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s));
   CUDA_CHECK(cudaEventRecord(x->ev0, s));
-  enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists);
+  enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists,
+                 nullptr, 1, tail);
   CUDA_CHECK(cudaEventRecord(x->ev1, s));
   x->search_pending = true;
   x->last_nq = nq;
@@ -753,6 +755,29 @@ int hnswb200_search_device_multi(hnswb200_index* x, const float* d_queries, int6
   });
 }
 
+int hnswb200_search_device_sharded(hnswb200_index* x, const float* d_queries, int64_t nq, int k, int ef, int mode, int shard,
+                                   int n_shards, int64_t first_row, int32_t* g_ids, float* g_dists, uint32_t* arrive, int n_final,
+                                   int32_t* const* f_ids, float* const* f_dists, void* stream) {
+  return guard([&] {
+    if (!x) fail(HNSWB200_EINVAL, "index is NULL");
+    if (n_shards < 1 || n_shards > 32 || shard < 0 || shard >= n_shards) fail(HNSWB200_EINVAL, "search_device_sharded: shard / n_shards out of range");
+    if (n_final < 1 || n_final > 8 || !f_ids || !f_dists || !g_ids || !g_dists || !arrive) fail(HNSWB200_EINVAL, "search_device_sharded: NULL buffer or n_final outside 1..8");
+    if (first_row < 0 || first_row + x->n > (int64_t(1) << 31) - 1) fail(HNSWB200_EINVAL, "search_device_sharded: global ids exceed int32");
+    if (nq > 0 && !d_queries) fail(HNSWB200_EINVAL, "search_device_sharded: queries is NULL");
+    std::lock_guard<std::mutex> lk(x->mu);
+    use_device(x);
+    hb::ShardTail t{};
+    t.n_shards = n_shards; t.shard = shard; t.id_offset = (int32_t)first_row;
+    t.g_ids = g_ids; t.g_dists = g_dists; t.arrive = arrive; t.n_final = n_final;
+    for (int r = 0; r < n_final; r++) {
+      if (!f_ids[r] || !f_dists[r]) fail(HNSWB200_EINVAL, "search_device_sharded: NULL destination");
+      t.f_ids[r] = f_ids[r]; t.f_dists[r] = f_dists[r];
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : x->stream;
+    search_device(x, padded_queries(x, d_queries, nq, s), nq, k, ef, mode, nullptr, nullptr, s, stream == nullptr, 0, nullptr, nullptr, &t);
+  });
+}
+
 int hnswb200_last_search_counters(hnswb200_index* x, uint32_t* out, int64_t nq) {
   return guard([&] {
     if (!x || !out) fail(HNSWB200_EINVAL, "index or out is NULL");
@@ -890,3 +915,4 @@ int hnswb200_host_unregister(const void* ptr) {
 
 #include "api_build.inl"
 #include "api_eval.inl"
+#include "api_sharded.inl"

@@ -27,6 +27,24 @@
 
 namespace hb {
 
+// Row-sharded index: every shard answers every query; the exchange and the merge of the
+// per-shard rows are the tail of the search kernel itself.  A warp stores its finished row (ids already
+// global) into the gather block of the HOME device — plain stores through a peer mapping over NVLink —
+// and bumps the query's arrival counter there with a system-scope atomic; the warp that finds itself
+// last (on whichever GPU it runs) reads the n_shards rows back and writes the merged row to every
+// final destination.  No all-gather, no barrier between the shards, no separate merge launch.
+struct ShardTail {
+  int n_shards;              // 0: not sharded
+  int shard;
+  int32_t id_offset;         // first global row of this shard
+  int32_t* g_ids;            // home: [n_shards][nq][k]
+  float* g_dists;
+  unsigned int* arrive;      // home: [nq], zero before the call
+  int n_final;
+  int32_t* f_ids[8];         // [nq][k] each (any device)
+  float* f_dists[8];
+};
+
 struct SearchParams {
   GraphView g;
   const float* queries;      // [nq][ld4*4]
@@ -47,6 +65,7 @@ struct SearchParams {
   int n_peer_out;
   int32_t* peer_ids[8];
   float* peer_dists[8];
+  ShardTail tail;
   uint32_t* counters;        // [nq][3]
   unsigned int* next_query;  // work counter
   uint32_t* bitset_pool;     // [pool_size][words]
@@ -449,6 +468,58 @@ __device__ __forceinline__ void greedy_layer(const GraphView& g, WarpCtx<CPL, QR
   }
 }
 
+// see ShardTail.  keys[0..n) = this shard's beam, ascending.
+__device__ __forceinline__ void shard_tail(const SearchParams& p, unsigned qi, int lane, const uint64_t* keys, int n) {
+  const ShardTail& t = p.tail;
+  const GraphView& g = p.g;
+  const size_t nqk = (size_t)p.nq * p.k;
+  const size_t row = (size_t)qi * p.k;
+  for (int i = lane; i < p.k; i += 32) {
+    int32_t oid = -1;
+    float od = __int_as_float(0x7fc00000);
+    if (i < n) {
+      const uint64_t key = keys[i];
+      oid = (int32_t)key_id(key) + t.id_offset;
+      const float d = key_dist(key);
+      od = g.metric == 0 ? (float)sqrt((double)d) : d;
+    }
+    t.g_ids[(size_t)t.shard * nqk + row + i] = oid;
+    t.g_dists[(size_t)t.shard * nqk + row + i] = od;
+  }
+  __syncwarp();
+  __threadfence_system();
+  unsigned prev = 0;
+  if (lane == 0) prev = atomicAdd_system(t.arrive + qi, 1u);
+  prev = __shfl_sync(FULL, prev, 0);
+  if (prev + 1u != (unsigned)t.n_shards) return;
+  // last to arrive: S-way merge, lane s holds the head of shard s's row (merge.cuh does the same after an all-gather)
+  __threadfence_system();
+  const volatile int32_t* gi = t.g_ids;
+  const volatile float* gd = t.g_dists;
+  int head = 0;
+  const size_t base = (size_t)(lane < t.n_shards ? lane : 0) * nqk + row;
+  for (int j = 0; j < p.k; j++) {
+    uint64_t key = KEY_INF;
+    float myd = 0.f;
+    if (lane < t.n_shards && head < p.k) {
+      const int32_t id = gi[base + head];
+      myd = gd[base + head];
+      // rows hold the OUTPUT distance (sqrt for L2): monotone in the beam's order, ties broken by global id
+      if (id >= 0) key = make_key(myd, (uint32_t)id);
+    }
+    uint64_t mn = key;
+    for (int o = 16; o; o >>= 1) { uint64_t x = __shfl_xor_sync(FULL, mn, o); mn = x < mn ? x : mn; }
+    const unsigned who = __ballot_sync(FULL, key == mn && mn != KEY_INF);
+    const int src = who ? __ffs(who) - 1 : 0;
+    const float d = __shfl_sync(FULL, myd, src);
+    if (who && lane == src) head++;
+    if (lane < t.n_final) {
+      t.f_ids[lane][row + j] = who ? (int32_t)key_id(mn) : -1;
+      t.f_dists[lane][row + j] = who ? d : (p.pad_inf ? __int_as_float(0x7f800000) : __int_as_float(0x7fc00000));
+    }
+  }
+}
+
 template <int CPL>
 __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -529,6 +600,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
         p.peer_dists[r][(size_t)qi * p.k + i] = od;
       }
     }
+    if (p.tail.n_shards > 0) shard_tail(p, qi, lane, w.keys, n);
     if (lane == 0) {
       if (p.counters) {
         p.counters[(size_t)qi * 3 + 0] = n_dist;

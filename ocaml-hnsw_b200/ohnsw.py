@@ -35,6 +35,9 @@ class Hgraph:
             capi.check(capi.lib().hnswb200_set_flavour(self._h, flavour))
 
     def close(self):
+        if getattr(self, "_borrowed", None) is not None:      # a shard of a MultiGpuHgraph: the owner destroys it
+            self._h = None
+            return
         if getattr(self, "_h", None) and self._h and capi is not None and getattr(capi, "_lib", None) is not None:
             capi._lib.hnswb200_destroy(self._h)       # (at interpreter shutdown the module may already be gone)
             self._h = None

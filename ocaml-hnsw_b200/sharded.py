@@ -1,17 +1,23 @@
-"""Multi-GPU layer: one process per GPU, the dataset split into contiguous row shards.
+"""Multi-GPU layer: the dataset split into contiguous row shards, one per GPU.
 
 The reference has nothing distributed; this is the sharding BASELINE.json's
-north_star prescribes on top of the same `Ohnsw` entry points: every rank builds and searches
-the HNSW sub-graph of its own rows `[lo, hi)`, the query batch is the same on every rank, and
-the per-shard `[nq][k]` result rows are exchanged and merged by `hnswb200_merge_topk_device`
-(shard-local ids become global ids inside the merge).  The exchange is fused into the search
-kernel: every rank's warps store their finished rows straight into every peer's gather buffer
-(torch symmetric memory = peer-mapped HBM over NVLink / NVSwitch), so what follows the search is one
-device-side barrier and the merge — no all-gather.  Where symmetric memory is unavailable the
-exchange is ONE packed NCCL all-gather.  No collective runs during graph traversal or the build.
+north_star prescribes on top of the same `Ohnsw` entry points: every shard builds and searches
+the HNSW sub-graph of its own rows `[lo, hi)`, the query batch goes to every shard, and the
+per-shard `[nq][k]` result rows are merged into global top-k rows.  Exchange and merge are the tail
+of the search kernel itself (csrc/search.cuh, ShardTail): a warp stores its finished row — ids
+already global — into a gather block on the home GPU through the NVLink peer mapping and bumps the
+query's arrival counter there; the warp that arrives last merges the rows in place.  No all-gather,
+no merge launch.  No collective runs during graph traversal or the build.
 
-torch is plumbing here: device buffers for the exchange and `torch.distributed`.
+Two hosts for the same kernels:
+  * `MultiGpuHgraph` — ONE process drives every GPU through `hnswb200_sharded_*` (no torch, no NCCL):
+    what an OCaml or C host uses (examples/benchmark_c.c --gpus N).
+  * `ShardedHgraph` — one process per GPU (torchrun): buffers in torch symmetric memory, one device
+    barrier per step; where symmetric memory is unavailable, ONE packed NCCL all-gather followed by
+    `hnswb200_merge_topk_device`.  torch is plumbing here: peer-mapped buffers and `torch.distributed`.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _capi as capi
@@ -38,6 +44,74 @@ def gather_rows(local, world, group=None):
         # concatenated along dim 0 (the layout every backend accepts); `out` is the stacked view of it
         dist.all_gather_into_tensor(out.view((world * local.shape[0],) + tuple(local.shape[1:])), local.contiguous(), group=group)
     return out
+
+
+class MultiGpuHgraph:
+    """`Ohnsw.Hgraph` over every GPU of the box from one process (`hnswb200_sharded_*`, include/hnsw_b200.h)."""
+
+    def __init__(self, dim, distance=ohnsw.distance_l2, num_connections=16, num_nodes_search_construction=100, seed=0,
+                 devices=(0,)):
+        self._s = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        capi.check(capi.lib().hnswb200_sharded_create(C.byref(self._s), dim, distance, num_connections,
+                                                      num_nodes_search_construction, seed, len(devices), devs))
+        self.dim, self.n_shards = dim, len(devices)
+
+    def close(self):
+        if getattr(self, "_s", None) and self._s and capi is not None and getattr(capi, "_lib", None) is not None:
+            capi._lib.hnswb200_sharded_destroy(self._s)
+            self._s = None
+
+    __del__ = close
+
+    @staticmethod
+    def build_batch_bigarray(distance, batch, *, num_connections, num_nodes_search_construction, devices=(0,), levels=None,
+                             seed=0, params=None):
+        """Ohnsw.build_batch_bigarray (lib/ohnsw.ml:840-857) over all shards at once."""
+        batch = capi.as_mat(batch)
+        m = MultiGpuHgraph(batch.shape[1], distance, num_connections, num_nodes_search_construction, seed, devices)
+        for name, v in (params or {}).items():
+            m.set_param(name, v)
+        lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
+        capi.check(capi.lib().hnswb200_sharded_build(m._s, capi.ptr(batch), batch.shape[0], capi.ptr(lv)))
+        return m
+
+    def set_param(self, name, value):
+        capi.check(capi.lib().hnswb200_sharded_set_param(self._s, name.encode(), int(value)))
+
+    def knn_batch_bigarray(self, batch, *, k, ef=None, mode=capi.MODE_PARITY, out=None):
+        """Ohnsw.knn_batch_bigarray (lib/ohnsw.ml:877-897): global ids, rows ascending by (distance, id)."""
+        batch = capi.as_mat(batch, self.dim)
+        nq = batch.shape[0]
+        ids, dists = out if out is not None else (np.empty((nq, k), np.int32), np.empty((nq, k), np.float32))
+        capi.check(capi.lib().hnswb200_sharded_search(self._s, capi.ptr(batch), nq, k, k if ef is None else ef, mode,
+                                                      capi.ptr(ids), capi.ptr(dists)))
+        return ids, dists
+
+    def search_device(self, d_queries, nq, k, ef, d_ids, d_dists, stream=0, mode=capi.MODE_PARITY):
+        """All buffers on the first shard's device (ints = device pointers)."""
+        capi.check(capi.lib().hnswb200_sharded_search_device(self._s, d_queries, nq, k, ef, mode, d_ids, d_dists, stream or None))
+
+    def shard(self, i):
+        """(shard i as an Ohnsw.Hgraph borrowed from this handle, its first global row)."""
+        h, first = C.c_void_p(), C.c_int64()
+        capi.check(capi.lib().hnswb200_sharded_shard(self._s, i, C.byref(h), C.byref(first)))
+        g = ohnsw.Hgraph.__new__(ohnsw.Hgraph)
+        g._h, g.dim, g._borrowed = h, self.dim, self           # keeps the owner alive; never destroyed through this view
+        return g, first.value
+
+    def info(self):
+        out, ns = capi.Info(), C.c_int()
+        capi.check(capi.lib().hnswb200_sharded_get_info(self._s, C.byref(out), C.byref(ns)))
+        return out
+
+    def num_nodes(self):
+        return self.info().n
+
+    def stats(self):
+        out = capi.Stats()
+        capi.check(capi.lib().hnswb200_sharded_get_stats(self._s, C.byref(out)))
+        return out
 
 
 class ShardedHgraph:
@@ -68,21 +142,32 @@ class ShardedHgraph:
         return ShardedHgraph(h, n_total, rank, world, group)
 
     def _peer_buffers(self, nq, k, dev):
-        """Two gather buffers [world][2][nq][k] in symmetric memory (double buffered: a rank may start
-        writing step i+2 only after the barrier of step i+1, by which every rank has merged step i)."""
-        import ctypes as C
+        """Two symmetric-memory blocks (double buffered: the rows a call returns stay valid until the call after
+        next).  Layout in int32 words: gather rows [world][2][nq][k] | merged rows [2][nq][k] | arrival counters [nq].
+        Only rank 0's gather rows and counters are used (the home rank); the merged rows are stored into every
+        rank's block by whichever warp arrives last for a query."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group if self.group is not None else dist.group.WORLD
         out = []
+        nqk = nq * k
+        words = self.world * 2 * nqk + 2 * nqk + nq
         for _ in range(2):
-            t = symm_mem.empty((self.world, 2, nq, k), dtype=torch.int32, device=dev)
+            t = symm_mem.empty((words,), dtype=torch.int32, device=dev)
+            t.zero_()
             hdl = symm_mem.rendezvous(t, group)
-            block = 2 * nq * k * 4
-            ids_ptrs = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.rank * block for r in range(self.world)])
-            d_ptrs = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + self.rank * block + nq * k * 4 for r in range(self.world)])
-            out.append(dict(t=t, hdl=hdl, ids_ptrs=ids_ptrs, d_ptrs=d_ptrs))
+            home = int(hdl.buffer_ptrs[0])
+            fin = self.world * 2 * nqk * 4
+            f_ids = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + fin for r in range(self.world)])
+            f_d = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + fin + nqk * 4 for r in range(self.world)])
+            out.append(dict(t=t, hdl=hdl, g_ids=home, g_d=home + self.world * nqk * 4, arrive=home + fin + 2 * nqk * 4,
+                            f_ids=f_ids, f_d=f_d, out_ids=t[self.world * 2 * nqk:self.world * 2 * nqk + nqk].view(nq, k),
+                            out_d=t[self.world * 2 * nqk + nqk:self.world * 2 * nqk + 2 * nqk].view(torch.float32).view(nq, k),
+                            arrive_t=t[self.world * 2 * nqk + 2 * nqk:]))
+        torch.cuda.synchronize()
+        out[0]["hdl"].barrier(channel=0)
+        torch.cuda.synchronize()
         return out
 
     def _buffers(self, nq, k):
@@ -126,13 +211,17 @@ class ShardedHgraph:
             return b["ids"], b["d"]
         import torch.distributed as dist
         if self._peer is not None:
-            # fused exchange: the search kernel stores every finished row into all peers' buffers
-            pb = self._peer[self._step & 1]
+            # fused exchange + merge (ShardTail): rows go to rank 0's gather block, the last warp to arrive for a
+            # query merges and stores the global row into every rank's block; the barrier ends the step
+            pb, nxt = self._peer[self._step & 1], self._peer[(self._step + 1) & 1]
             self._step += 1
-            capi.check(capi.lib().hnswb200_search_device_multi(self.local._h, q_dev.data_ptr(), nq, k, k if ef is None else ef,
-                                                               mode, self.world, pb["ids_ptrs"], pb["d_ptrs"], stream))
+            if self.rank == 0:
+                nxt["arrive_t"].zero_()            # counters of the NEXT call; ordered before this call's barrier
+            capi.check(capi.lib().hnswb200_search_device_sharded(
+                self.local._h, q_dev.data_ptr(), nq, k, k if ef is None else ef, mode, self.rank, self.world,
+                int(self.offsets[self.rank]), pb["g_ids"], pb["g_d"], pb["arrive"], self.world, pb["f_ids"], pb["f_d"], stream))
             pb["hdl"].barrier(channel=0)
-            g = pb["t"]
+            return pb["out_ids"], pb["out_d"]
         else:
             self.local.search_device(q_dev.data_ptr(), nq, k, k if ef is None else ef, b["ids"].data_ptr(), b["d"].data_ptr(),
                                      stream=stream, mode=mode)

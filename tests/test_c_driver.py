@@ -42,3 +42,14 @@ def test_c_driver_runs_the_benchmark_recipe(tmp_path):
     recall = float(r.stdout.strip().splitlines()[-1].split()[1])
     assert recall >= 0.9
     assert "max_layer" in r.stdout and "distance evaluations per query" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_driver_sharded_without_python(tmp_path):
+    """--shards 4: the multi-GPU entry points (hnswb200_sharded_*) from plain C, four shards on device 0; with
+    --gpus N the same binary spreads them over N GPUs."""
+    exe = _compile(tmp_path)
+    r = subprocess.run([exe, "--shards", "4", "20000", "64", "200", "16", "100", "10", "50"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "4 shards on device 0" in r.stdout
+    assert float(r.stdout.strip().splitlines()[-1].split()[1]) >= 0.9
