@@ -91,6 +91,8 @@ def lib():
                 "hnsw_b200 has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("HNSWB200_LIB") and not hasattr(L, name):
+                continue                       # an older tuning build named by the override: A/B probes only
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L

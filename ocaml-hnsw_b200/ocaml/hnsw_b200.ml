@@ -21,6 +21,7 @@ external build_ : index -> Lacaml.S.mat -> i32vec -> unit = "hb_build"
 external insert_ : index -> Lacaml.S.mat -> i32vec -> unit = "hb_insert"
 external search_ : index -> Lacaml.S.mat -> int -> int -> i32mat -> Lacaml.S.mat -> unit = "hb_search_byte" "hb_search"
 external info : index -> int * int * int = "hb_info"
+external params : index -> int * int = "hb_params"            (* num_connections, num_nodes_search_construction *)
 external bruteforce_ : Lacaml.S.mat -> Lacaml.S.mat -> int -> Lacaml.S.mat -> unit = "hb_bruteforce"
 external pin : ('a, 'b, 'c) Bigarray.Genarray.t -> unit = "hb_pin"
 external unpin : ('a, 'b, 'c) Bigarray.Genarray.t -> unit = "hb_unpin"
@@ -38,6 +39,27 @@ module Ohnsw = struct
     type t = unit                      (* visited sets live in GPU shared memory, per query *)
     let create (_ : int) = ()
   end
+  (* lib/ohnsw.ml:6-12 *)
+  module HeapElt = struct
+    type t = { node : int; distance : float }
+  end
+  (* The result queue of Ohnsw.knn (lib/ohnsw.ml:404-416): abstract, popped in ascending distance.  Only the
+     operations a caller of knn uses on its result are offered (pop_min, iter, copy). *)
+  module MinQueue : sig
+    type 'a t
+    type element = HeapElt.t
+    val of_sorted : element list -> 'a t
+    val pop_min : 'a t -> element option
+    val iter : 'a t -> f:(element -> unit) -> unit
+    val copy : 'a t -> 'a t
+  end = struct
+    type 'a t = { mutable rest : HeapElt.t list }
+    type element = HeapElt.t
+    let of_sorted rest = { rest }
+    let pop_min q = match q.rest with [] -> None | e :: tl -> q.rest <- tl; Some e
+    let iter q ~f = List.iter f q.rest
+    let copy q = { rest = q.rest }
+  end
 
   let distance_l2 = L2                                                     (* lib/ohnsw.ml:899 *)
 
@@ -49,9 +71,15 @@ module Ohnsw = struct
     build_ h batch no_levels;
     h
 
-  (* lib/ohnsw.ml:766-837; M, efC and level_mult were fixed at creation *)
-  let insert (h : _ Hgraph.t) (target : Lacaml.S.vec) ~num_connections:_ ~num_nodes_search_construction:_
-      (_level_mult : float) (_ : Visited.t) =
+  (* lib/ohnsw.ml:766-837; M, efC and level_mult (= 1 / ln M, :844) were fixed at creation: the reference passes
+     the same values on every call, other values are rejected *)
+  let insert (h : _ Hgraph.t) (target : Lacaml.S.vec) ~num_connections ~num_nodes_search_construction
+      (level_mult : float) (_ : Visited.t) =
+    let (m_, efc_) = params h in
+    if num_connections <> m_ then invalid_arg "insert: num_connections differs from the index's";
+    if num_nodes_search_construction <> efc_ then invalid_arg "insert: num_nodes_search_construction differs from the index's";
+    if Float.abs (level_mult -. 1. /. log (float_of_int m_)) > 1e-9 *. level_mult then
+      invalid_arg "insert: level_mult differs from 1 / ln num_connections";
     let m = Lacaml.S.Mat.of_col_vecs [| target |] in
     insert_ h m no_levels
 
@@ -64,18 +92,20 @@ module Ohnsw = struct
     let ids = Array.init nq (fun j -> Array.init k (fun i -> Int32.to_int ids32.{j, i})) in
     ids, distances
 
-  (* lib/ohnsw.ml:859-875: the result min-queue as an ascending (node, distance) list *)
-  let knn (h : _ Hgraph.t) (_ : Visited.t) ~k (target : Lacaml.S.vec) =
+  (* lib/ohnsw.ml:859-875: the result as a MinQueue.t, popped nearest first *)
+  let knn (h : _ Hgraph.t) (_ : Visited.t) ~k (target : Lacaml.S.vec) : _ MinQueue.t =
     let ids, d = knn_batch_bigarray h ~k (Lacaml.S.Mat.of_col_vecs [| target |]) in
-    List.filter (fun (i, _) -> i >= 0) (List.init k (fun i -> ids.(0).(i), d.{i + 1, 1}))
+    MinQueue.of_sorted
+      (List.filter (fun (e : HeapElt.t) -> e.node >= 0)
+         (List.init k (fun i -> { HeapElt.node = ids.(0).(i); distance = d.{i + 1, 1} })))
 end
 
 (* Hnsw.Ba = MakeBatch(EuclideanBa), lib/hnsw.ml:729-778, 817-819 *)
 module Ba = struct
   type t = index
   type value = Lacaml.S.vec
-  let build ~num_neighbours ~num_neighbours_build (data : Lacaml.S.mat) : t =
-    let h = create (Lacaml.S.Mat.dim1 data) 0 num_neighbours num_neighbours_build 0 0 in
+  let build ?(seed = 0) ?(device = 0) ~num_neighbours ~num_neighbours_build (data : Lacaml.S.mat) : t =
+    let h = create (Lacaml.S.Mat.dim1 data) 0 num_neighbours num_neighbours_build seed device in
     set_flavour h 1;
     build_ h data no_levels;
     h

@@ -3,4 +3,5 @@
 #define MOCK_CAML_ALLOC_H
 #include "mlvalues.h"
 value caml_alloc_tuple(uintnat n);
+value caml_copy_double(double d);
 #endif

@@ -9,5 +9,6 @@
 #define CAMLparam5(a, b, c, d, e) value* caml__roots5[] = {&(a), &(b), &(c), &(d), &(e)}; (void)caml__roots5
 #define CAMLxparam1(a) value* caml__xroots1[] = {&(a)}; (void)caml__xroots1
 #define CAMLlocal1(a) value a = Val_unit
+#define CAMLlocal2(a, b) value a = Val_unit, b = Val_unit
 #define CAMLreturn(x) return (x)
 #endif

@@ -19,4 +19,5 @@ typedef intnat value;
 #define Field(v, i) (((value*)(v))[i])
 void caml_modify(value* fp, value v);
 #define Store_field(b, i, v) caml_modify(&Field((b), (i)), (v))
+#define Wosize_val(v) ((uintnat)(((uintnat*)(v))[-1] >> 10))
 #endif

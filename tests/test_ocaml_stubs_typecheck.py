@@ -43,11 +43,16 @@ def _arity(ml_type):
 
 
 def test_every_external_has_a_stub_of_the_right_arity():
-    ml = open(os.path.join(OCAML, "hnsw_b200.ml")).read()
+    ml = open(os.path.join(OCAML, "hnsw_b200.ml")).read() + open(os.path.join(OCAML, "hnsw_b200_graph.ml")).read()
+    ml = re.sub(r"^(\s*external [^\n=]*)\n\s*(= )", r"\1 \2", ml, flags=re.M)      # externals written over two lines
+    ml = re.sub(r"^\s+external ", "external ", ml, flags=re.M)                        # externals inside a module
     c = open(os.path.join(OCAML, "hnsw_b200_stubs.c")).read()
     stubs = {m.group(1): m.group(2) for m in re.finditer(r"CAMLprim value (\w+)\(([^)]*)\)", c)}
     externals = re.findall(r"^external (\w+) : (.+?) = ((?:\"\w+\"\s*)+)$", ml, re.M)
-    assert len(externals) >= 10
+    assert len(externals) >= 22
+    names = {n for n, _, _ in externals}
+    for needed in ("import_graph_", "export_layer_", "export_levels_", "stats_", "create_", "search_"):
+        assert needed in names, needed
     for name, ml_type, syms in externals:
         syms = re.findall(r"\"(\w+)\"", syms)
         n = _arity(ml_type)
