@@ -48,9 +48,12 @@ extern "C" {
 #define HNSWB200_IP 2
 
 /* search mode.  PARITY reproduces the reference's sequential best-first search id for id
- * (one expansion per iteration, exact visited set, (distance,id) tie order).  FAST is reserved
- * for a relaxed traversal (same result contract, no id parity); this version runs the PARITY
- * kernel for both. */
+ * (one expansion per iteration, exact visited set, (distance,id) tie order).  FAST expands the two
+ * best unexpanded candidates per iteration on layer 0 (their rows fetched together, their new
+ * neighbours evaluated in one batch): half as many dependent iterations; same result contract
+ * (k rows ascending, exact distances), same stop rule, recall not lower, but NO id parity — a query
+ * may visit a few nodes the reference's loop would not.  Indexes with more than 32 layer-0 slots
+ * per row (M > 16) run the PARITY traversal in both modes. */
 #define HNSWB200_MODE_PARITY 0
 #define HNSWB200_MODE_FAST 1
 

@@ -21,6 +21,7 @@
 #include "bruteforce.cuh"
 #include "bruteforce_tc.cuh"
 #include "merge.cuh"
+#include "stats.cuh"
 
 namespace {
 
@@ -279,7 +280,10 @@ int stage_ahead_for(const hnswb200_index* x) {
   return x->param_stage_ahead >= 0 ? (int)std::min<int64_t>(x->param_stage_ahead, 31) : 8;
 }
 
-SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
+// MODE_FAST doubles the expansions per iteration where a layer-0 row is one 32-slot chunk (M <= 16)
+bool fast_mode(const hnswb200_index* x, int mode) { return mode == HNSWB200_MODE_FAST && x->slots0 <= 32; }
+
+SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq, int mode = HNSWB200_MODE_PARITY) {
   SearchPlan pl;
   int chunks = x->ld / 4;
   int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
@@ -290,7 +294,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 8) : round_up(std::max(1024, 42 * ef), 128);
   int eb = hash_entry_bytes(x, hs, x->n);                        // 2 (16-bit quotiented entries) or 4
-  pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
+  pl.nb_cap = (std::max(x->slots0, x->slotsU) > 32 || fast_mode(x, mode)) ? 64 : 32;     // list slots gathered per pass
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes;
@@ -405,8 +409,10 @@ void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
 void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_queries, int64_t nq, int k, int ef,
                     int32_t* d_ids, float* d_dists, uint32_t* counters, unsigned int* next, cudaStream_t s,
                     int n_peer = 0, int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr,
-                    const unsigned int* ready = nullptr, unsigned int ready_step = 1, const hb::ShardTail* tail = nullptr) {
+                    const unsigned int* ready = nullptr, unsigned int ready_step = 1, const hb::ShardTail* tail = nullptr,
+                    int mode = HNSWB200_MODE_PARITY) {
   hb::SearchParams p;
+  p.fast = fast_mode(x, mode) && pl.nb_cap >= 64;
   p.ready = ready; p.ready_step = ready_step;
   if (tail) p.tail = *tail; else p.tail.n_shards = 0;
   p.g = x->view();
@@ -456,7 +462,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
                    int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr, const hb::ShardTail* tail = nullptr) {
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
-  SearchPlan pl = plan_search(x, ef, nq);
+  SearchPlan pl = plan_search(x, ef, nq, mode);
   // the work counter, events and per-query counters are per-index scratch: a search enqueued on another
   // stream waits for the previous one (calls on one index are serialised on the device as on the host)
   if (x->search_pending) CUDA_CHECK(cudaStreamWaitEvent(s, x->ev1, 0));
@@ -469,7 +475,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s));
   CUDA_CHECK(cudaEventRecord(x->ev0, s));
   enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists,
-                 nullptr, 1, tail);
+                 nullptr, 1, tail, mode);
   CUDA_CHECK(cudaEventRecord(x->ev1, s));
   x->search_pending = true;
   x->last_nq = nq;
@@ -492,7 +498,7 @@ constexpr int HOST_CHUNKS = 8;
 void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int ef, int mode, int32_t* ids, float* dists) {
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
-  SearchPlan pl = plan_search(x, ef, nq);
+  SearchPlan pl = plan_search(x, ef, nq, mode);
   if (x->search_pending) CUDA_CHECK(cudaStreamWaitEvent(x->stream, x->ev1, 0));
   ensure_pool(x, pl.grid * pl.warps, x->n, x->stream);
   if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));
@@ -518,7 +524,8 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   if (C == 1) {
     upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, s0);
     CUDA_CHECK(cudaEventRecord(x->ev0, s0));
-    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0);
+    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
+                   nullptr, 1, nullptr, mode);
   } else {
     // One kernel, started at once; the queries stream in behind it in C pieces on the copy stream,
     // each followed by a 4-byte "pieces ready" update the kernel's warps wait on (bounded) before
@@ -529,7 +536,7 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
     CUDA_CHECK(cudaStreamWaitEvent(sc, x->aux_event[0], 0));          // counters are zero before any piece lands
     CUDA_CHECK(cudaEventRecord(x->ev0, s0));
     enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
-                   x->d_next.p + 1, step);
+                   x->d_next.p + 1, step, nullptr, mode);
     for (int c = 0; c < C; c++) {
       const int64_t q0 = (int64_t)step * c, m = std::min<int64_t>(step, nq - q0);
       if (m <= 0) break;
@@ -864,18 +871,25 @@ int hnswb200_get_stats(hnswb200_index* x, hnswb200_stats* out) {
                                   (double)x->last_nq * (4.0 * x->dim + 8.0 * x->last_k);
     // Hgraph.Stats (lib/hnsw.ml:353-375); recomputed only after the graph changed
     st.num_layers = x->n ? x->max_layer + 1 : 0;
-    for (int l = 0; x->layer_stats_dirty && l < st.num_layers && l < 16; l++) {
-      std::vector<int32_t> rows; int slots = 0;
-      download_layer(x, l, rows, slots);
-      int64_t nodes = 0, iso = 0, sum = 0; int mn = 1 << 30, mx = -1;
-      for (int64_t i = 0; i < x->n; i++) {
-        const int32_t* row = layer_row(x, l, rows, slots, i);
-        if (!row) continue;
-        int d = row_degree(row, slots);
-        nodes++; sum += d; mn = std::min(mn, d); mx = std::max(mx, d); if (!d) iso++;
+    if (x->layer_stats_dirty && st.num_layers > 0) {
+      // a reduction on the device (stats.cuh): 5 numbers per layer come back, not the adjacency arrays
+      const int L = std::min(st.num_layers, 16);
+      std::vector<hb::LayerStats> hs((size_t)L);
+      for (auto& r : hs) { r.nodes = r.degree_sum = r.isolated = 0; r.min_degree = 0x7fffffff; r.max_degree = -1; }
+      DevBuf<hb::LayerStats> ds;
+      ds.reserve((size_t)L);
+      CUDA_CHECK(cudaMemcpy(ds.p, hs.data(), hs.size() * sizeof(hb::LayerStats), cudaMemcpyHostToDevice));
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * 8, (x->n + 255) / 256));
+      hb::layer_stats_kernel<<<grid, 256, 0, x->stream>>>(x->view(), x->level.p, L, ds.p);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaStreamSynchronize(x->stream));
+      CUDA_CHECK(cudaMemcpy(hs.data(), ds.p, hs.size() * sizeof(hb::LayerStats), cudaMemcpyDeviceToHost));
+      st.gpu_launches += 1;
+      for (int l = 0; l < L; l++) {
+        const hb::LayerStats& r = hs[(size_t)l];
+        st.layer_nodes[l] = (int64_t)r.nodes; st.layer_min_degree[l] = r.nodes ? r.min_degree : 0; st.layer_max_degree[l] = r.nodes ? r.max_degree : 0;
+        st.layer_mean_degree[l] = r.nodes ? (double)r.degree_sum / (double)r.nodes : 0.0; st.layer_isolated[l] = (int64_t)r.isolated;
       }
-      st.layer_nodes[l] = nodes; st.layer_min_degree[l] = nodes ? mn : 0; st.layer_max_degree[l] = nodes ? mx : 0;
-      st.layer_mean_degree[l] = nodes ? (double)sum / (double)nodes : 0.0; st.layer_isolated[l] = iso;
     }
     x->layer_stats_dirty = false;
     *out = st;
