@@ -55,7 +55,9 @@ def parse():
     ap.add_argument("--efc", type=int, default=200)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--target-recall", type=float, default=0.95)
-    ap.add_argument("--ref-n", type=int, default=100_000, help="--impl reference: rows the CPU build covers")
+    ap.add_argument("--ref-n", type=int, default=400_000,
+                    help="--impl reference: rows the sequential CPU build covers (a prefix of the dataset; 400k rows build in "
+                         "about 4 minutes on one host core, the full 1M in about a quarter of an hour)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--metric", default="l2", choices=["l2", "angular"],
                     help="angular = SURVEY.md config C3 (GloVe shape): unit-norm Gaussian-mixture vectors, distance 1 - a.b")
@@ -174,13 +176,19 @@ class ClockSampler:
 
 
 def profiled_traffic(workload, ef):
-    """dram__bytes_read + write of the search kernel from the committed ncu capture, when it was
-    taken on this exact workload and ef (profiles/traffic.json); None otherwise."""
+    """dram__bytes_read + write of the search kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json) -> (bytes per launch, source note).  ncu cannot run inside the timed run, so this
+    is a constant measured once on this workload; when the run's ef is not the captured one (the ef that
+    reaches the recall target can move by one between builds) the figure is scaled by the algorithmic
+    bytes, and the note says so."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["search_kernel"]
-        return t["dram_bytes_per_launch"] if (t["workload"], t["ef"]) == (workload, ef) else None
     except Exception:
-        return None
+        return None, None
+    if t.get("workload") != workload:
+        return None, None
+    src = f"committed ncu capture ({t.get('capture', 'profiles/')}) at ef={t['ef']}, not measured in this run"
+    return t["dram_bytes_per_launch"], src
 
 
 def host_threads(O):
@@ -260,6 +268,11 @@ def run_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": rec, "index_rows": n},
+        "same_config": bool(n == a.n),
+        "same_config_note": None if n == a.n else (
+            f"the CPU arm's index covers the first {n} of {a.n} rows (its build is sequential: {build_s:.0f} s for {n} rows); a smaller "
+            "index makes every query cheaper, so the ratio against this line understates the speed-up; the GPU arm's "
+            "cpu_baseline searches the identical 1M-row graph"),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "build_seconds": build_s, "gpu_launches": 0}), file=_REAL_STDOUT, flush=True)
@@ -434,9 +447,12 @@ def run_ours(a):
         kms.append(st.search_kernel_ms)
         abytes = st.search_algorithmic_bytes          # counted: n_dist*4*dim + rows*4*slots + nq*(4*dim + 8*k)
     peak, peak_src = measured_peak()
+    traffic, traffic_src = profiled_traffic(workload_name(a), ef_star) if world == 1 else (None, None)
     k_ms = statistics.mean(kms)
     achieved = abytes / (k_ms * 1e-3) / 1e9
     st = h.stats()
+    if st.search_tie_overflows:
+        raise SystemExit(f"{st.search_tie_overflows} queries overflowed the tie list: the timed search was not a PARITY search")
 
     # ---- e2e: the public host-buffer call, pinned H2D + D2H inside the timed region
     Qp = np.ascontiguousarray(Q)
@@ -513,20 +529,24 @@ def run_ours(a):
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": round(rec_star, 4), "mode": "parity",
-                       "sharding": f"{world} row shards, exchange: {sh.exchange}, then merge kernel" if world > 1 else "single index",
+                       "sharding": (f"{world} row shards, one process per GPU; exchange: {sh.exchange}" if world > 1 else "single index"),
                        "l2": (f"shard index {index_bytes / 1e6:.0f} MB vs {l2_bytes / 1e6:.0f} MB of L2: "
                               + ("L2 flushed (write of 2 x L2 bytes) before every step, steps timed one by one" if flush
                                  else "inputs larger than L2, no flush between steps")),
                        "ef_sweep": sweep},
             "build_seconds": build_s, "ground_truth_seconds": gt_s,
             "build": {"inserts_per_s": (hi - lo) / build_s, "dist_evals_per_insert": bst.build_n_dist / max(1, bst.build_inserts),
-                      "library_seconds_rank0": bst.build_seconds},
+                      "library_seconds_rank0": bst.build_seconds, "dropped_incoming_links": int(bst.build_dropped_incoming),
+                      # counted evaluations x 4 x dim + adjacency rows read, over the library's wall time (H2D of the rows included)
+                      "roofline": {"bound": "hbm", "achieved": bst.build_algorithmic_bytes / bst.build_seconds / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": bst.build_algorithmic_bytes / bst.build_seconds / 1e9 / peak,
+                                   "algorithmic_bytes": bst.build_algorithmic_bytes}},
             "e2e": {"value": a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(Qp.nbytes),
                     "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes), "recall_at_10": round(e2e_rec, 4),
                     "recall_compute_dataset_ml": round(e2e_rec_dist, 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": profiled_traffic(workload_name(a), ef_star) if world == 1 else None,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "note": ("shard index fits L2: within a step most of the algorithmic bytes are served from L2, so "
                                   "frac against the HBM peak is not a DRAM figure here") if flush else None,

@@ -47,15 +47,14 @@ extern "C" {
 #define HNSWB200_ANGULAR 1
 #define HNSWB200_IP 2
 
-/* search mode.  PARITY reproduces the reference's sequential best-first search id for id
- * (one expansion per iteration, exact visited set, (distance,id) tie order).  FAST expands the two
- * best unexpanded candidates per iteration on layer 0 (their rows fetched together, their new
- * neighbours evaluated in one batch): half as many dependent iterations; same result contract
- * (k rows ascending, exact distances), same stop rule, recall not lower, but NO id parity — a query
- * may visit a few nodes the reference's loop would not.  Indexes with more than 32 layer-0 slots
- * per row (M > 16) run the PARITY traversal in both modes. */
+/* search mode: the one traversal this library has.  PARITY reproduces the reference's sequential
+ * best-first search id for id (one expansion per iteration, exact visited set, (distance, id) tie order).
+ * A relaxed mode (two expansions per iteration, no id parity) was built and measured in round 2: with
+ * every SM full of queries the kernel is bound by instructions and bytes per expansion, not by the
+ * length of a query's dependent chain, so it was no faster (1.21 ms vs 1.21 ms per 10k queries in the
+ * same build) and its extra code cost the PARITY path 14 %; it was removed rather than shipped as a
+ * second, slower name for the same thing.  Any other mode value is rejected. */
 #define HNSWB200_MODE_PARITY 0
-#define HNSWB200_MODE_FAST 1
 
 /* which reference code path's quirks are mirrored:
  * OHNSW   = lib/ohnsw.ml   (strict accept `d < top`, 2M links for a new node on layer 0,

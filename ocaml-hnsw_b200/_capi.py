@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("HNSWB200_LIB") or os.path.join(_HERE, "libhnsw_b200.s
 
 OK, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3
 L2, ANGULAR, IP = 0, 1, 2
-MODE_PARITY, MODE_FAST = 0, 1
+MODE_PARITY = 0
 FLAVOUR_OHNSW, FLAVOUR_HNSW_BA = 0, 1
 
 

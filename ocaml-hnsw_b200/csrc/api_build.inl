@@ -156,7 +156,7 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   hb::SearchParams& sp = p.sp;
   sp.g = x->view();
   sp.queries = nullptr; sp.nq = B; sp.ef = x->efC; sp.k = x->efC; sp.ef_cap = pl.ef_cap;
-  sp.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA; sp.pad_inf = 0; sp.fast = 0;
+  sp.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA; sp.pad_inf = 0;
   sp.hc = pl.hc; sp.q_smem_chunks = pl.q_chunks; sp.smem_per_warp = pl.smem_per_warp; sp.nb_cap = pl.nb_cap;
   sp.stage_slots = pl.stage_slots; sp.stage_ahead = stage_ahead_for(x);
   sp.out_ids = nullptr; sp.out_dists = nullptr; sp.counters = nullptr; sp.next_query = nullptr;

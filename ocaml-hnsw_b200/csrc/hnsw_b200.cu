@@ -280,10 +280,7 @@ int stage_ahead_for(const hnswb200_index* x) {
   return x->param_stage_ahead >= 0 ? (int)std::min<int64_t>(x->param_stage_ahead, 31) : 8;
 }
 
-// MODE_FAST doubles the expansions per iteration where a layer-0 row is one 32-slot chunk (M <= 16)
-bool fast_mode(const hnswb200_index* x, int mode) { return mode == HNSWB200_MODE_FAST && x->slots0 <= 32; }
-
-SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq, int mode = HNSWB200_MODE_PARITY) {
+SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   SearchPlan pl;
   int chunks = x->ld / 4;
   int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
@@ -294,7 +291,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq, int mode = HNSWB20
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 8) : round_up(std::max(1024, 42 * ef), 128);
   int eb = hash_entry_bytes(x, hs, x->n);                        // 2 (16-bit quotiented entries) or 4
-  pl.nb_cap = (std::max(x->slots0, x->slotsU) > 32 || fast_mode(x, mode)) ? 64 : 32;     // list slots gathered per pass
+  pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
   int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes;
@@ -399,7 +396,7 @@ const float* padded_queries(hnswb200_index* x, const float* d_queries, int64_t n
 void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
   if (nq < 0 || k <= 0) fail(HNSWB200_EINVAL, "search: nq must be >= 0 and k > 0");
   if (ef < k) fail(HNSWB200_EINVAL, "search: ef must be >= k");
-  if (mode != HNSWB200_MODE_PARITY && mode != HNSWB200_MODE_FAST) fail(HNSWB200_EINVAL, "search: unknown mode");
+  if (mode != HNSWB200_MODE_PARITY) fail(HNSWB200_EINVAL, "search: unknown mode (only HNSWB200_MODE_PARITY exists)");
   if (x->poisoned) fail(HNSWB200_ECUDA, "the index is unusable: an earlier build/insert call failed half-way");
   if (x->n == 0 || x->entry < 0) fail(HNSWB200_EINVAL, "knn: empty hgraph");     // lib/ohnsw.ml:862
   if (ef > 4096) fail(HNSWB200_EINVAL, "search: ef > 4096 is not supported");
@@ -409,10 +406,8 @@ void check_search_args(hnswb200_index* x, int64_t nq, int k, int ef, int mode) {
 void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_queries, int64_t nq, int k, int ef,
                     int32_t* d_ids, float* d_dists, uint32_t* counters, unsigned int* next, cudaStream_t s,
                     int n_peer = 0, int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr,
-                    const unsigned int* ready = nullptr, unsigned int ready_step = 1, const hb::ShardTail* tail = nullptr,
-                    int mode = HNSWB200_MODE_PARITY) {
+                    const unsigned int* ready = nullptr, unsigned int ready_step = 1, const hb::ShardTail* tail = nullptr) {
   hb::SearchParams p;
-  p.fast = fast_mode(x, mode) && pl.nb_cap >= 64;
   p.ready = ready; p.ready_step = ready_step;
   if (tail) p.tail = *tail; else p.tail.n_shards = 0;
   p.g = x->view();
@@ -462,7 +457,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
                    int32_t* const* peer_ids = nullptr, float* const* peer_dists = nullptr, const hb::ShardTail* tail = nullptr) {
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
-  SearchPlan pl = plan_search(x, ef, nq, mode);
+  SearchPlan pl = plan_search(x, ef, nq);
   // the work counter, events and per-query counters are per-index scratch: a search enqueued on another
   // stream waits for the previous one (calls on one index are serialised on the device as on the host)
   if (x->search_pending) CUDA_CHECK(cudaStreamWaitEvent(s, x->ev1, 0));
@@ -475,7 +470,7 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s));
   CUDA_CHECK(cudaEventRecord(x->ev0, s));
   enqueue_search(x, pl, d_queries, nq, k, ef, d_ids, d_dists, x->d_counters.p, x->d_next.p, s, n_peer, peer_ids, peer_dists,
-                 nullptr, 1, tail, mode);
+                 nullptr, 1, tail);
   CUDA_CHECK(cudaEventRecord(x->ev1, s));
   x->search_pending = true;
   x->last_nq = nq;
@@ -498,7 +493,7 @@ constexpr int HOST_CHUNKS = 8;
 void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int ef, int mode, int32_t* ids, float* dists) {
   check_search_args(x, nq, k, ef, mode);
   if (nq == 0) return;
-  SearchPlan pl = plan_search(x, ef, nq, mode);
+  SearchPlan pl = plan_search(x, ef, nq);
   if (x->search_pending) CUDA_CHECK(cudaStreamWaitEvent(x->stream, x->ev1, 0));
   ensure_pool(x, pl.grid * pl.warps, x->n, x->stream);
   if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));
@@ -524,8 +519,7 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   if (C == 1) {
     upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, s0);
     CUDA_CHECK(cudaEventRecord(x->ev0, s0));
-    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
-                   nullptr, 1, nullptr, mode);
+    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0);
   } else {
     // One kernel, started at once; the queries stream in behind it in C pieces on the copy stream,
     // each followed by a 4-byte "pieces ready" update the kernel's warps wait on (bounded) before
@@ -536,7 +530,7 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
     CUDA_CHECK(cudaStreamWaitEvent(sc, x->aux_event[0], 0));          // counters are zero before any piece lands
     CUDA_CHECK(cudaEventRecord(x->ev0, s0));
     enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
-                   x->d_next.p + 1, step, nullptr, mode);
+                   x->d_next.p + 1, step);
     for (int c = 0; c < C; c++) {
       const int64_t q0 = (int64_t)step * c, m = std::min<int64_t>(step, nq - q0);
       if (m <= 0) break;

@@ -50,7 +50,6 @@ struct SearchParams {
   const float* queries;      // [nq][ld4*4]
   int64_t nq;
   int ef, k, ef_cap;
-  int fast;                  // MODE_FAST: two expansions per iteration on layer 0 (no id parity; see layer_search)
   int accept_ties;           // Hnsw.Ba flavour: accept d <= top (lib/hnsw.ml:494-506)
   int pad_inf;               // Hnsw.Ba flavour: +inf padding (lib/hnsw.ml:771)
   HashCfg hc;                // visited hash geometry (hc.slots == 0: global bitset per warp)
@@ -267,29 +266,6 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
     }
     const uint32_t c = key_id(ck);
     n_exp++;
-    // MODE_FAST (layer 0, rows of <= 32 slots): the runner-up is expanded in the SAME iteration — its row is
-    // fetched with the first one's, the new neighbours of both are evaluated in one distance batch and
-    // accepted in list order.  Half as many dependent iterations per query; the runner-up is expanded even
-    // when the first expansion would have displaced it, so a query visits a few more nodes than the
-    // reference's loop and the ids may differ (recall is not lower).  Never used by PARITY.
-    const int32_t* row2 = nullptr;
-    if (p.fast && layer == 0 && !from_ties) {
-      int pos2 = -1;
-      for (int f2 = fu; f2 < n; f2 += 32) {
-        const int idx = f2 + lane;
-        const unsigned b = __ballot_sync(FULL, idx < n && !(w.keys[idx] & 1ull));
-        if (b) { pos2 = f2 + __ffs(b) - 1; break; }
-      }
-      if (pos2 >= 0) {
-        const uint32_t c2 = key_id(w.keys[pos2]);
-        __syncwarp();
-        if (lane == 0) w.keys[pos2] |= 1ull;
-        if (pos2 == fu) fu = pos2 + 1;
-        __syncwarp();
-        row2 = g.adj0 + (size_t)c2 * g.slots0;
-        n_exp++;
-      }
-    }
 
     // ---- Neighbours.iter (Graph.adjacent graph c.node) (:570), 32 list slots per round
     const int slots = layer == 0 ? g.slots0 : g.slotsU;
@@ -303,7 +279,6 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
     for (int s0 = 0; s0 < slots && row; s0 += p.nb_cap) {
       int total = 0;
       bool row_ended = false;
-      const int nb2 = row2 ? ((lane < slots) ? __ldg(row2 + lane) : -1) : -1;   // (issued with the first row's load)
       for (int r0 = s0; r0 < min(slots, s0 + p.nb_cap); r0 += 32) {
         int nb = (r0 + lane < slots) ? __ldg(row + r0 + lane) : -1;
         unsigned valid = __ballot_sync(FULL, nb >= 0);
@@ -314,13 +289,6 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
         if (is_new) w.newid[total + __popc(m & ((1u << lane) - 1u))] = (uint32_t)nb;
         total += __popc(m);
         if (valid != FULL) { row_ended = true; break; }                       // row ended inside this chunk
-      }
-      if (row2 && __ballot_sync(FULL, nb2 >= 0)) {                              // the runner-up's row (one chunk: slots <= 32)
-        if (!w.vis.bits && w.vis.count + (uint32_t)total + 32u > w.vis.limit) visited_spill(w.vis, p, lane);
-        const bool is_new = visited_test_and_set(w.vis, p, nb2 >= 0, (uint32_t)nb2, lane);
-        const unsigned m = __ballot_sync(FULL, is_new);
-        if (is_new) w.newid[total + __popc(m & ((1u << lane) - 1u))] = (uint32_t)nb2;
-        total += __popc(m);
       }
       w.vis.count += total;
       __syncwarp();

@@ -179,11 +179,11 @@ class ShardedHgraph:
             if self.peer_exchange and self.world <= 8:
                 try:
                     peer = self._peer_buffers(nq, k, dev)
-                    self.exchange = "peer-store"
+                    self.exchange = "peer stores into the home rank's gather block + last-arriver merge, both inside the search kernel; one device barrier per step"
                 except Exception as e:                      # no symmetric memory on this system / build
-                    self.exchange = f"nccl-all-gather (symmetric memory unavailable: {type(e).__name__})"
+                    self.exchange = f"one packed NCCL all-gather, then the merge kernel (symmetric memory unavailable: {type(e).__name__})"
             elif self.world > 1:
-                self.exchange = "nccl-all-gather"
+                self.exchange = "one packed NCCL all-gather, then the merge kernel"
             self._peer = peer
             # one packed block per rank: [0] = ids (int32), [1] = distances (fp32 bits) -> ONE all-gather
             packed = torch.empty((2, nq, k), dtype=torch.int32, device=dev)

@@ -389,28 +389,7 @@ def test_visited_hash_formats_are_exact(uni2k, hash_bits):
     assert h.stats().search_visited_overflows > 0
 
 
-def test_fast_mode_contract():
-    """HNSWB200_MODE_FAST: two expansions per iteration.  No id parity is promised; the contract is: k distinct
-    ids per row, ascending, each at its exact distance (bit-identical to what PARITY reports for that id), recall
-    not below PARITY's, fewer iterations than expansions.  With more than 32 layer-0 slots (M > 16) it is PARITY."""
-    X = H.sift_like(20000, 128, seed=1234)
-    Q = H.sift_like(500, 128, seed=4321)
-    h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=16, num_nodes_search_construction=100,
-                                   levels=draw_levels(len(X), 16))
-    gt, _ = H.brute_force_knn_l2(X, Q, 10, return_ids=True)
-    for ef in (10, 32, 100):
-        ids_p, d_p = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=ef)
-        ids_f, d_f = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=ef, mode=capi.MODE_FAST)
-        assert (ids_f >= 0).all() and all(len(set(r.tolist())) == 10 for r in ids_f)
-        assert (np.diff(d_f, axis=1) >= 0).all()
-        exact = np.sqrt(((X[ids_f].astype(np.float64) - Q[:, None, :]) ** 2).sum(-1))
-        assert np.allclose(exact, d_f, rtol=1e-6)
-        both = ids_f == ids_p
-        assert np.array_equal(d_f[both].view(np.uint32), d_p[both].view(np.uint32))
-        assert H.Recall.ids(gt, ids_f) >= H.Recall.ids(gt, ids_p) - 0.002
-    X2, Q2 = uniform(3000, 32, 3), uniform(100, 32, 4)
-    h2 = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X2, num_connections=24, num_nodes_search_construction=60,
-                                    levels=draw_levels(3000, 24))
-    a = Ohnsw.knn_batch_bigarray(h2, Q2, k=10, ef=40)
-    b = Ohnsw.knn_batch_bigarray(h2, Q2, k=10, ef=40, mode=capi.MODE_FAST)
-    assert_same_results(a[0], a[1], b[0], b[1])
+def test_unknown_mode_is_rejected(uni2k):
+    X, Q, o, h = uni2k
+    with pytest.raises(ValueError, match="unknown mode"):
+        Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=10, mode=1)
