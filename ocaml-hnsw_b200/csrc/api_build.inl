@@ -67,11 +67,12 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   int chunks = x->ld / 4;
   int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
   pl.cpl = cpl <= 4 ? cpl : 0;
-  pl.q_chunks = pl.cpl ? 0 : round_up(chunks, 2);
+  pl.q_chunks = pl.cpl ? hb::TEAM * pl.cpl : round_up(chunks, 2);      // (a gang reads the target from shared memory)
+  pl.gang = 1;
   pl.ef_cap = round_up(ef, 32);
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
-  int extra = pl.q_chunks * 16 + bp.sel_cap * 4 + stage_bytes;
+  int extra = pl.q_chunks * 16 + bp.sel_cap * 4 + stage_bytes + hb::GANG_JOB_BYTES;
   int hs = x->param_hash_slots > 0 ? round_up((int)x->param_hash_slots, 8) : round_up(std::max(1024, 32 * ef), 128);
   const int eb = hash_entry_bytes(x, hs, n_total);
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;
@@ -159,6 +160,15 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   sp.accept_ties = x->flavour == HNSWB200_FLAVOUR_HNSW_BA; sp.pad_inf = 0;
   sp.hc = pl.hc; sp.q_smem_chunks = pl.q_chunks; sp.smem_per_warp = pl.smem_per_warp; sp.nb_cap = pl.nb_cap;
   sp.stage_slots = pl.stage_slots; sp.stage_ahead = stage_ahead_for(x);
+  // a batch that leaves most resident warps idle: a gang of warps per insert (the largest of 8, 4, 2 that
+  // divides the CTA and still gives every insert of the batch a gang at once)
+  int gang = 1;
+  if (!pl.stage_slots && x->param_build_batch != 1 && x->param_gang != 1) {
+    const int64_t capacity = (int64_t)pl.grid * pl.warps;
+    for (int P = 8; P >= 2; P >>= 1)
+      if (pl.warps % P == 0 && B * P <= capacity && (x->param_gang == 0 || P <= x->param_gang)) { gang = P; break; }
+  }
+  sp.gang = gang;
   sp.out_ids = nullptr; sp.out_dists = nullptr; sp.counters = nullptr; sp.next_query = nullptr;
   sp.bitset_pool = x->d_bitpool.p; sp.pool_busy = x->d_pool_busy.p; sp.pool_size = x->pool_size; sp.words = x->pool_words;
   sp.events = x->d_events.p;
@@ -175,7 +185,8 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
   g_trace.start();
   g_trace.batches++;
   if (B < (int64_t)pl.grid * pl.warps) g_trace.small++;
-  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (B + pl.warps - 1) / pl.warps));
+  const int per_cta = pl.warps / gang;             // inserts a CTA works on at a time
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (B + per_cta - 1) / per_cta));
   switch (pl.cpl) {
     case 1: launch_build_search<1>(p, pl, grid, s); break;
     case 2: launch_build_search<2>(p, pl, grid, s); break;

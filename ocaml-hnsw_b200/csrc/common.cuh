@@ -216,6 +216,32 @@ __device__ __forceinline__ void batch_dist(const GraphView& g, const float4* q, 
   __syncwarp();
 }
 
+// The rounds first, first + step, ... of batch_dist (round r = vectors 8r .. 8r+7): the share of one warp when
+// several warps evaluate one batch (search.cuh, Gang).  The target is the shared copy qs.  Same arithmetic
+// per vector as batch_dist, so which warp evaluates a vector does not change its distance.
+template <int CPL>
+__device__ __forceinline__ void batch_dist_rounds(const GraphView& g, const float4* qs, const uint32_t* ids, float* d,
+                                                  int cnt, int lane, int first, int step) {
+  const int tl = lane & (TEAM - 1), team = lane >> 3;
+  for (int base = 8 * first; base < cnt; base += 8 * step) {
+    if (base + 4 < cnt) {
+      const int j0 = base + team, j1 = base + 4 + team;
+      const int node[2] = {(int)ids[j0], (int)ids[min(j1, cnt - 1)]};
+      float o[2];
+      team_dist<CPL, 2>(g, nullptr, qs, node, tl, o);
+      if (tl == 0) d[j0] = o[0];
+      if (tl == 4 && j1 < cnt) d[j1] = o[1];
+    } else {
+      const int j0 = base + team;
+      const int node[1] = {(int)ids[min(j0, cnt - 1)]};
+      float o[1];
+      team_dist<CPL, 1>(g, nullptr, qs, node, tl, o);
+      if (tl == 0 && j0 < cnt) d[j0] = o[0];
+    }
+  }
+  __syncwarp();
+}
+
 // ---- high-dimension rows: bulk-copy (1-D TMA) staged gather ---------------------------------------
 // Rows of >= STAGE_MIN_BYTES (dim >= 256) are not fetched with per-lane LDG: one elected lane issues
 // one `cp.async.bulk` per row (a single UBLKCP instruction moves a whole 3 840-byte GIST row) into a

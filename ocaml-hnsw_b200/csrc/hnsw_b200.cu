@@ -98,6 +98,7 @@ struct hnswb200_index {
   int64_t param_host_chunks = 0;
   int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
   int64_t param_stage_ahead = -1;       // rows beyond the ring prefetched to L2 (-1 auto, 0..31)
+  int64_t param_gang = 0;               // warps per query: 0 auto (1 when the batch fills the GPU), 1, 2, 4
   int64_t param_hash_bits = 0;          // visited hash entries: 0 auto (16-bit quotiented when the id range allows), 16, 32
   unsigned int* h_ready = nullptr;      // pinned: the "pieces ready" values the copy stream writes after each piece
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -174,6 +175,7 @@ struct SearchPlan {
   int cpl, warps, ef_cap, hash_slots, q_chunks, smem_per_warp, grid, nb_cap;
   hb::HashCfg hc;        // visited hash geometry for hash_slots entries
   int stage_slots;      // bulk-copy ring of this many rows per warp (0: LDG gathers)
+  int gang;             // warps per query (search.cuh, Gang)
   size_t smem;
 };
 
@@ -294,7 +296,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   pl.nb_cap = std::max(x->slots0, x->slotsU) > 32 ? 64 : 32;     // list slots gathered per pass
   pl.stage_slots = stage_slots_for(x, pl.cpl);
   const int stage_bytes = pl.stage_slots ? hb::stage_smem_bytes(pl.stage_slots, chunks) : 0;
-  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes;
+  int fixed = hb::search_smem_per_warp(pl.ef_cap, 0, pl.q_chunks, pl.nb_cap) + stage_bytes + hb::GANG_JOB_BYTES;
   if (fixed + 1024 * 4 > x->max_smem_optin) fail(HNSWB200_EINVAL, "ef too large for shared memory");
   // 16-bit entries cost a few more instructions per test-and-set: only where 32-bit ones would leave
   // fewer warps resident than the register file allows (ef >~ 42 at 128 dimensions)
@@ -312,7 +314,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   pl.hash_slots = hs;
   pl.hc = make_hash_cfg(x, hs, x->n);
   if (force32 && pl.hc.bits16) { pl.hc.bits16 = 0; pl.hc.bytes = (uint32_t)hs * 4u; }
-  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, (int)pl.hc.bytes, pl.q_chunks, pl.nb_cap) + stage_bytes;
+  pl.smem_per_warp = hb::search_smem_per_warp(pl.ef_cap, (int)pl.hc.bytes, pl.q_chunks, pl.nb_cap) + stage_bytes + hb::GANG_JOB_BYTES;
   // A batch small enough to be resident all at once (one warp per query, nq <= SMs x warps per SM) gets the
   // deepest ring with which it still is: every query then runs from the first cycle, in CTAs of one warp so
   // the SMs hold the same number of queries (1 000 GIST queries: 7 per SM with a 6-row ring).
@@ -343,6 +345,23 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
     warps = std::max(1, warps);
   }
   while (warps > 1 && (size_t)warps * pl.smem_per_warp > (size_t)x->max_smem_optin) warps--;
+  // A batch that leaves most of the GPU's warps without a query gets a gang of 2 or 4 warps per query
+  // (search.cuh, Gang): one CTA per query, the distance rounds of an expansion shared among its warps.
+  pl.gang = 1;
+  if (!pl.stage_slots) {
+    const int64_t capacity = (int64_t)x->num_sms * per_sm_warps;
+    if (x->param_gang > 0) pl.gang = (int)x->param_gang;
+    else if (nq * 4 <= capacity) pl.gang = 4;
+    else if (nq * 2 <= capacity) pl.gang = 2;
+  }
+  if (pl.gang > 1) {
+    pl.warps = pl.gang;
+    pl.smem = (size_t)pl.smem_per_warp;
+    int per_sm = search_resident(pl.cpl, pl.warps * 32, pl.smem);
+    per_sm = std::min(per_sm, std::max(1, per_sm_warps / pl.gang));
+    pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * per_sm, nq));
+    return pl;
+  }
   pl.warps = warps;
   pl.smem = (size_t)warps * pl.smem_per_warp;
   int per_sm = search_resident(pl.cpl, warps * 32, pl.smem);
@@ -417,6 +436,7 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   p.hc = pl.hc; p.q_smem_chunks = pl.q_chunks; p.smem_per_warp = pl.smem_per_warp; p.nb_cap = pl.nb_cap;
   p.stage_slots = pl.stage_slots;
   p.stage_ahead = stage_ahead_for(x);
+  p.gang = pl.gang;
   p.out_ids = d_ids; p.out_dists = d_dists; p.counters = counters;
   p.n_peer_out = n_peer;
   for (int r = 0; r < n_peer; r++) { p.peer_ids[r] = peer_ids[r]; p.peer_dists[r] = peer_dists[r]; }
@@ -424,11 +444,11 @@ void enqueue_search(hnswb200_index* x, const SearchPlan& pl, const float* d_quer
   p.pool_size = x->pool_size; p.words = x->pool_words; p.events = x->d_events.p;
   p.tie_pool = x->d_tie_pool.p; p.tie_busy = x->d_tie_busy.p; p.tie_slots = TIE_SLOTS; p.tie_cap = TIE_CAP;
   SearchPlan q = pl;
-  q.grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, (nq + pl.warps - 1) / pl.warps));
+  q.grid = (int)std::max<int64_t>(1, std::min<int64_t>(pl.grid, pl.gang > 1 ? nq : (nq + pl.warps - 1) / pl.warps));
   static const bool trace = std::getenv("HNSWB200_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "[hnsw_b200 search] nq=%lld ef=%d cpl=%d grid=%d x %d warps, %d B smem/warp (hash %d slots, ring %d rows), visited %s\n",
-            (long long)nq, ef, pl.cpl, q.grid, pl.warps, pl.smem_per_warp, pl.hash_slots, pl.stage_slots,
+    fprintf(stderr, "[hnsw_b200 search] nq=%lld ef=%d cpl=%d grid=%d x %d warps, %d B smem/warp (hash %d slots, ring %d rows), gang %d, visited %s\n",
+            (long long)nq, ef, pl.cpl, q.grid, pl.warps, pl.smem_per_warp, pl.hash_slots, pl.stage_slots, pl.gang,
             pl.hash_slots ? (pl.hc.bits16 ? "hash16" : "hash32") : "bitset");
   switch (pl.cpl) {
     case 1: launch_search<1>(p, q, s); break;
@@ -696,6 +716,10 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "stage_rows") x->param_stage_rows = value;
     else if (s == "stage_ahead") x->param_stage_ahead = value;
     else if (s == "hash_bits") x->param_hash_bits = value;
+    else if (s == "gang") {
+      if (value != 0 && value != 1 && value != 2 && value != 4) fail(HNSWB200_EINVAL, "gang must be 0 (automatic), 1, 2 or 4");
+      x->param_gang = value;
+    }
     else if (s == "row_floats") {             // vector row stride in floats (multiple of 4, >= dim); only on an empty index
       if (x->n != 0) fail(HNSWB200_EINVAL, "row_floats can only be set on an empty index");
       if (value < x->dim || value % 4 != 0) fail(HNSWB200_EINVAL, "row_floats must be a multiple of 4 and >= dim");

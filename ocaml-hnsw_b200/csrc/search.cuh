@@ -57,6 +57,7 @@ struct SearchParams {
   int q_smem_chunks;         // float4 slots reserved for the query copy
   int stage_slots;           // > 0: rows are staged through a per-warp bulk-copy ring of this many rows (common.cuh)
   int stage_ahead;           // rows beyond the ring prefetched to L2
+  int gang;                  // warps per query (1, 2 or 4): see Gang
   int smem_per_warp;
   int32_t* out_ids;          // [nq][k] or null
   float* out_dists;          // [nq][k]
@@ -87,11 +88,52 @@ struct SearchParams {
 __host__ __device__ inline int search_smem_per_warp(int ef_cap, int hash_bytes, int q_chunks, int nb_cap = 32) {
   return ef_cap * 8 + TIES_CAP * 8 + nb_cap * 4 + nb_cap * 4 + q_chunks * 16 + hash_bytes;
 }
+constexpr int GANG_JOB_BYTES = 32;      // sizeof(GangJob), at the very end of a gang's block
 // the bulk-copy ring (when used) follows the fixed part of the warp's block
 __device__ __forceinline__ void stage_attach(Stage& st, unsigned char* at, int slots, int ahead, int ld4, int lane) {
   float4* ring = slots > 0 ? reinterpret_cast<float4*>(at) : nullptr;
   uint64_t* bar = slots > 0 ? reinterpret_cast<uint64_t*>(at + (size_t)slots * ld4 * 16) : nullptr;
   stage_init(st, ring, bar, slots, ahead, lane);
+}
+
+// ---- a gang: several warps on one query / insert --------------------------------------------------------
+// When a batch is smaller than the warps the GPU holds (a build batch early in the build, a replica's
+// share of the queries, a single Ohnsw.knn) one warp per item leaves the machine idle and the item's
+// dependent chain — row, visited, 3-4 distance rounds, merge — sets the time.  A gang of P warps then
+// works on ONE item: warp 0 runs the traversal exactly as a lone warp does, and hands every distance
+// batch of more than one round to all P warps (round r goes to warp r mod P); the others wait on a
+// named barrier between batches.  Distances do not depend on who evaluates them, so the result is the
+// lone warp's, bit for bit.
+struct GangJob {
+  const uint32_t* ids;
+  float* d;
+  const float4* target;
+  int cnt;                   // < 0: no more work, the helpers leave
+  int pad;
+};
+struct Gang {
+  int P, rank, bar;          // warps in the gang, this warp's place, named barrier (1..15)
+  GangJob* job;              // shared
+};
+__device__ __forceinline__ void gang_sync(const Gang& gg) {
+  asm volatile("bar.sync %0, %1;" ::"r"(gg.bar), "r"(gg.P * 32) : "memory");
+}
+// helpers' loop: evaluate the rounds that fall to this warp until the leader says stop
+template <int CPL>
+__device__ __forceinline__ void gang_help(const GraphView& g, const Gang& gg, int lane) {
+  while (true) {
+    gang_sync(gg);
+    const int cnt = gg.job->cnt;
+    if (cnt < 0) return;
+    batch_dist_rounds<CPL>(g, gg.job->target, gg.job->ids, gg.job->d, cnt, lane, gg.rank, gg.P);
+    gang_sync(gg);
+  }
+}
+__device__ __forceinline__ void gang_dismiss(const Gang& gg, int lane) {
+  if (gg.P <= 1) return;
+  if (lane == 0) gg.job->cnt = -1;
+  __syncwarp();
+  gang_sync(gg);
 }
 
 // QREG: the target vector lives in registers (CPL float4 per lane); otherwise in shared memory
@@ -108,6 +150,7 @@ struct WarpCtx {
   Stage st;
   uint64_t* tie_spill;       // non-null while this warp holds a region of the tie pool
   int tie_slot;
+  Gang gang;
   int lane;
   __device__ __forceinline__ const float4* target_regs() const { return (CPL > 0 && QREG) ? q : nullptr; }
 };
@@ -295,12 +338,26 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
       if (total) {
         // every vector beyond the first round of eight starts moving towards L2 now, so the
         // later rounds of batch_dist wait for L2, not for HBM
+        if (w.gang.P > 1 && total > 8 && !w.st.ring) {
+          // the whole gang evaluates this batch (w.qs holds the target); rounds beyond the first P are sent for first
+          for (int j = lane; j < total; j += 32)
+            if (j >= 8 * w.gang.P) {
+              const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[j] * g.ld4 * 16;
+              for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
+            }
+          if (lane == 0) { w.gang.job->ids = w.newid; w.gang.job->d = w.newd; w.gang.job->target = w.qs; w.gang.job->cnt = total; }
+          __syncwarp();
+          gang_sync(w.gang);
+          batch_dist_rounds<CPL>(g, w.qs, w.newid, w.newd, total, lane, 0, w.gang.P);
+          gang_sync(w.gang);
+        } else {
         for (int j = lane; j < total && !w.st.ring; j += 32)
           if (j >= 8) {
             const char* vrow = reinterpret_cast<const char*>(g.vec) + (size_t)w.newid[j] * g.ld4 * 16;
             for (int b = 0; b < g.ld4 * 16; b += 128) prefetch_l2(vrow + b);
           }
         batch_dist<CPL>(g, w.target_regs(), w.qs, w.newid, w.newd, total, lane, &w.st);   // MinQueue.element (:573)
+        }
         n_dist += total;
       }
       for (int g0 = 0; g0 < total; g0 += 32) {
@@ -525,9 +582,12 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GraphView& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* my = smem_raw + (size_t)warp * p.smem_per_warp;
+  unsigned char* my = smem_raw + (size_t)(warp / p.gang) * p.smem_per_warp;        // one block per gang (per warp when gang == 1)
   WarpCtx<CPL, HB_SEARCH_QREG> w;
   w.lane = lane;
+  w.gang.P = p.gang; w.gang.rank = warp % p.gang; w.gang.bar = 1 + warp / p.gang;
+  w.gang.job = reinterpret_cast<GangJob*>(my + p.smem_per_warp - (int)sizeof(GangJob));
+  if (w.gang.rank > 0) { gang_help<CPL>(g, w.gang, lane); return; }
   w.keys = reinterpret_cast<uint64_t*>(my);
   w.ties = w.keys + p.ef_cap;
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
@@ -612,6 +672,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     visited_release(w.vis, p, lane);
     __syncwarp();
   }
+  gang_dismiss(w.gang, lane);
 }
 
 }  // namespace hb

@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 with_oracle = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
 gen = sys.argv[3] if len(sys.argv) > 3 else "sift"
 nq = 2000
-M, efC = 16, 100
+M, efC = 16, (int(sys.argv[4]) if len(sys.argv) > 4 else 100)
 if gen == "sift":
     X = H.sift_like(n, 128, seed=1234); Q = H.sift_like(nq, 128, seed=4321)
 else:
@@ -23,7 +23,7 @@ efs = (10, 16, 32, 64, 128)
 if with_oracle:
     t = time.time(); o = O.VecOracle(128).build(X, M, efC, lv); print("oracle build s", time.time() - t, flush=True)
     print("oracle ", " ".join(f"{H.Recall.ids(gt, o.search_mt(Q, 10, ef)[0]):.4f}" for ef in efs), flush=True)
-for ratio, batch in [(16, 16384), (32, 16384), (64, 16384), (128, 16384), (16, 1024), (10**9, 1)][: (6 if n <= 20000 else 4)]:
+for ratio, batch in [(16, 16384), (32, 16384), (48, 16384), (64, 16384), (128, 16384), (16, 1024), (10**9, 1)][: (7 if n <= 20000 else 5)]:
     h = Ohnsw.Hgraph(128, Ohnsw.distance_l2, M, efC)
     h.set_param("build_ratio", ratio); h.set_param("build_batch", batch)
     t = time.time()

@@ -366,3 +366,18 @@ def test_100k_batched_build_drops_no_incoming_link(built100k):
     st = h.stats()
     assert st.build_dropped_incoming == 0       # rows that received more than LINK_MCAP new nodes in one batch
     _check_structure(h.export_graph(), lv, 16)
+
+
+def test_gang_build_is_the_one_warp_build():
+    """Small build batches run a gang of warps per insert (shared distance rounds).  Nothing an insert computes
+    depends on the gang size, so the graph must be the graph of the one-warp-per-insert build, bit for bit."""
+    X = H.sift_like(30000, 128, seed=77)
+    lv = draw_levels(len(X), 16)
+    gs = []
+    for gang in (1, 0, 2):
+        h = Ohnsw.Hgraph(128, Ohnsw.distance_l2, 16, 100)
+        h.set_param("gang", gang)
+        capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), len(X), capi.ptr(lv)))
+        gs.append(h.export_graph())
+    for g in gs[1:]:
+        _same_graph(g, gs[0])

@@ -393,3 +393,32 @@ def test_unknown_mode_is_rejected(uni2k):
     X, Q, o, h = uni2k
     with pytest.raises(ValueError, match="unknown mode"):
         Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=10, mode=1)
+
+
+@pytest.mark.parametrize("gang", [2, 4])
+def test_gang_of_warps_per_query_is_exact(uni2k, gang):
+    """Several warps per query (search.cuh, Gang): warp 0 runs the traversal, the distance rounds of every
+    expansion are shared among the gang.  Rows and work counters must be the oracle's, whatever the gang."""
+    X, Q, o, _ = uni2k
+    h = _gpu_from(o, X, 16, 100)
+    h.set_param("gang", gang)
+    for k, ef in [(10, 10), (10, 50), (10, 200), (100, 512)]:
+        _check(o, h, Q, k, ef)
+    _check(o, h, Q[:1], 10, 64)                           # one query (Ohnsw.knn): the automatic choice is a gang too
+    h.set_param("hash_slots", 1024)                       # visited set spilling under a gang
+    _check(o, h, Q, 10, 200)
+    # tie-heavy integer data and 48-slot rows (two 32-slot chunks per expansion)
+    rng = np.random.default_rng(11)
+    Xi = rng.integers(0, 4, (3000, 16)).astype(np.float32)
+    Qi = rng.integers(0, 4, (200, 16)).astype(np.float32)
+    oi = _oracle_index(Xi, 24, 40)
+    hi = _gpu_from(oi, Xi, 24, 40)
+    hi.set_param("gang", gang)
+    for k, ef in [(10, 10), (10, 40), (5, 100)]:
+        _check(oi, hi, Qi, k, ef)
+
+
+def test_small_batches_pick_a_gang_automatically(uni2k):
+    X, Q, o, h = uni2k
+    for nq in (1, 7, 300):
+        _check(o, h, Q[:nq], 10, 32)
