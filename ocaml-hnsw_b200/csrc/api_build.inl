@@ -104,8 +104,13 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
 
 template <int CPL>
 void launch_build_search(const hb::BuildParams& p, const SearchPlan& pl, int grid, cudaStream_t s) {
-  CUDA_CHECK(cudaFuncSetAttribute(hb::build_search_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  hb::build_search_kernel<CPL><<<grid, pl.warps * 32, pl.smem, s>>>(p);
+  if (p.sp.gang > 1) {
+    CUDA_CHECK(cudaFuncSetAttribute(hb::build_search_kernel<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hb::build_search_kernel<CPL, true><<<grid, pl.warps * 32, pl.smem, s>>>(p);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(hb::build_search_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hb::build_search_kernel<CPL><<<grid, pl.warps * 32, pl.smem, s>>>(p);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 template <int CPL>

@@ -109,7 +109,7 @@ __device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* c
 }
 
 // ---- phase 1 --------------------------------------------------------------------------------------
-template <int CPL>
+template <int CPL, bool GANG = false>
 __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SearchParams& p = bp.sp;
@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // batches smaller than the resident warps run a gang of p.gang warps per insert (search.cuh, Gang): the
   // distance rounds of every expansion are shared, the insert's latency — which is the batch's — drops
-  unsigned char* my = smem_raw + (size_t)(warp / p.gang) * bp.smem_per_warp;
+  unsigned char* my = smem_raw + (size_t)(GANG ? warp / p.gang : warp) * bp.smem_per_warp;
   WarpCtx<CPL> w;
   w.lane = lane;
-  w.gang.P = p.gang; w.gang.rank = warp % p.gang; w.gang.bar = 1 + warp / p.gang;
+  w.gang.P = GANG ? p.gang : 1; w.gang.rank = GANG ? warp % p.gang : 0; w.gang.bar = GANG ? 1 + warp / p.gang : 1;
   w.gang.job = reinterpret_cast<GangJob*>(my + bp.smem_per_warp - (int)sizeof(GangJob));
-  if (w.gang.rank > 0) { gang_help<CPL>(g, w.gang, lane); return; }
+  if (GANG && w.gang.rank > 0) { gang_help<CPL>(g, w.gang, lane); return; }
   w.keys = reinterpret_cast<uint64_t*>(my);
   w.ties = w.keys + p.ef_cap;
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     if (b >= (unsigned)bp.B) break;
     const uint32_t v = (uint32_t)bp.n0 + b;
     load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)v * g.ld4, w.q, w.qs, lane);
-    if (CPL > 0 && p.gang > 1)                      // the gang reads the target from shared memory
+    if (GANG && CPL > 0)                            // the gang reads the target from shared memory
       load_target_smem(g, reinterpret_cast<const float4*>(g.vec) + (size_t)v * g.ld4, w.qs, p.q_smem_chunks, lane);
     const int lv = bp.level[v];
     uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
       }
       w.vis.count = n;
       __syncwarp();
-      layer_search(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
+      layer_search<CPL, true, GANG>(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
       visited_release(w.vis, p, lane);
       __syncwarp();
       // select_neighbours (MinQueue.copy w_queue) nc (:818-819)
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     tot_exp += n_exp0 + n_expU;
     if (tie_overflow && lane == 0) atomicAdd(p.events + 3, 1ull);
   }
-  gang_dismiss(w.gang, lane);
+  if (GANG) gang_dismiss(w.gang, lane);
   if (lane == 0) {
     atomicAdd(bp.counters + 0, tot_dist);
     atomicAdd(bp.counters + 1, tot_exp);

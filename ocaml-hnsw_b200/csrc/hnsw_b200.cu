@@ -181,24 +181,34 @@ struct SearchPlan {
 
 // resident CTAs per SM of the persistent search kernel (registers and shared memory both count);
 // cached: the query costs two driver calls
-int search_resident(int cpl, int threads, size_t smem) {
+int search_resident(int cpl, int threads, size_t smem, bool gang = false) {
   static std::mutex mu;
   static std::map<std::tuple<int, int, size_t>, int> cache;
   std::lock_guard<std::mutex> lk(mu);
-  auto key = std::make_tuple(cpl, threads, smem);
+  auto key = std::make_tuple(cpl + (gang ? 100 : 0), threads, smem);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   int nb = 0;
   switch (cpl) {
 #define HB_CASE(C)                                                                                              \
     case C:                                                                                                     \
-      CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<C>, threads, smem));      \
+      if (gang) {                                                                                               \
+        CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<C, true>, threads, smem)); \
+      } else {                                                                                                  \
+        CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<C>, threads, smem));    \
+      }                                                                                                         \
       break;
     HB_CASE(1) HB_CASE(2) HB_CASE(3) HB_CASE(4)
     default:
-      CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<0>, threads, smem));
+      if (gang) {
+        CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<0, true>, threads, smem));
+      } else {
+        CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hb::search_kernel<0>, threads, smem));
+      }
 #undef HB_CASE
   }
   cache[key] = std::max(1, nb);
@@ -357,7 +367,7 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   if (pl.gang > 1) {
     pl.warps = pl.gang;
     pl.smem = (size_t)pl.smem_per_warp;
-    int per_sm = search_resident(pl.cpl, pl.warps * 32, pl.smem);
+    int per_sm = search_resident(pl.cpl, pl.warps * 32, pl.smem, true);
     per_sm = std::min(per_sm, std::max(1, per_sm_warps / pl.gang));
     pl.grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)x->num_sms * per_sm, nq));
     return pl;
@@ -373,8 +383,13 @@ SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
 
 template <int CPL>
 void launch_search(const hb::SearchParams& p, const SearchPlan& pl, cudaStream_t s) {
-  CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  hb::search_kernel<CPL><<<pl.grid, pl.warps * 32, pl.smem, s>>>(p);
+  if (pl.gang > 1) {
+    CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hb::search_kernel<CPL, true><<<pl.grid, pl.warps * 32, pl.smem, s>>>(p);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(hb::search_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hb::search_kernel<CPL><<<pl.grid, pl.warps * 32, pl.smem, s>>>(p);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 

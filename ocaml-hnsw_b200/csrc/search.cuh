@@ -250,7 +250,7 @@ __device__ __forceinline__ void tie_release(W& w, const SearchParams& p, int lan
 
 // search_k (lib/ohnsw.ml:543-588) on layer `layer`, beam already seeded with `n` keys (all
 // unexpanded, all marked visited).  Leaves the nearest set in keys[0..n).
-template <int CPL, bool QREG>
+template <int CPL, bool QREG, bool GANG = false>
 __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL, QREG>& w, int layer, int& n,
                                              uint32_t& n_dist, uint32_t& n_exp, bool& tie_overflow) {
   const GraphView& g = p.g;
@@ -338,7 +338,7 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
       if (total) {
         // every vector beyond the first round of eight starts moving towards L2 now, so the
         // later rounds of batch_dist wait for L2, not for HBM
-        if (w.gang.P > 1 && total > 8 && !w.st.ring) {
+        if (GANG && total > 8) {
           // the whole gang evaluates this batch (w.qs holds the target); rounds beyond the first P are sent for first
           for (int j = lane; j < total; j += 32)
             if (j >= 8 * w.gang.P) {
@@ -577,17 +577,18 @@ __device__ __forceinline__ void shard_tail(const SearchParams& p, unsigned qi, i
   }
 }
 
-template <int CPL>
+// GANG: p.gang (2 or 4) warps per query, one query per CTA (the one-warp-per-query instance carries no gang code)
+template <int CPL, bool GANG = false>
 __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const GraphView& g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* my = smem_raw + (size_t)(warp / p.gang) * p.smem_per_warp;        // one block per gang (per warp when gang == 1)
+  unsigned char* my = smem_raw + (size_t)(GANG ? 0 : warp) * p.smem_per_warp;      // one block per warp, or one for the gang
   WarpCtx<CPL, HB_SEARCH_QREG> w;
   w.lane = lane;
-  w.gang.P = p.gang; w.gang.rank = warp % p.gang; w.gang.bar = 1 + warp / p.gang;
+  w.gang.P = GANG ? p.gang : 1; w.gang.rank = GANG ? warp : 0; w.gang.bar = 1;
   w.gang.job = reinterpret_cast<GangJob*>(my + p.smem_per_warp - (int)sizeof(GangJob));
-  if (w.gang.rank > 0) { gang_help<CPL>(g, w.gang, lane); return; }
+  if (GANG && w.gang.rank > 0) { gang_help<CPL>(g, w.gang, lane); return; }
   w.keys = reinterpret_cast<uint64_t*>(my);
   w.ties = w.keys + p.ef_cap;
   w.newid = reinterpret_cast<uint32_t*>(w.ties + TIES_CAP);
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     visited_test_and_set(w.vis, p, lane == 0, cur, lane);
     w.vis.count = 1;
     __syncwarp();
-    layer_search(p, w, 0, n, n_dist, n_exp0, tie_overflow);
+    layer_search<CPL, HB_SEARCH_QREG, GANG>(p, w, 0, n, n_dist, n_exp0, tie_overflow);
 
     // ---- pop ascending into the result rows (:886-893)
     for (int i = lane; i < p.k; i += 32) {
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(128, HB_SEARCH_MINB) search_kernel(const Searc
     visited_release(w.vis, p, lane);
     __syncwarp();
   }
-  gang_dismiss(w.gang, lane);
+  if (GANG) gang_dismiss(w.gang, lane);
 }
 
 }  // namespace hb

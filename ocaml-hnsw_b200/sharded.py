@@ -115,56 +115,82 @@ class MultiGpuHgraph:
 
 
 class ShardedHgraph:
-    """`Ohnsw.Hgraph` over a row-sharded dataset.  `n_total` rows exist across the group; this rank
-    owns `shard_range(n_total, rank, world)`."""
+    """`Ohnsw.Hgraph` over `world` GPUs, one process each, as S row shards x R replicas (S * R = world).
 
-    def __init__(self, local, n_total, rank, world, group=None, peer_exchange=True):
+    Rank r is shard s = r % S of replica group g = r // S.  The rows are cut into S contiguous shards (a replica
+    group holds the whole dataset); a batch of queries is cut into R contiguous slices, group g answers slice g —
+    every shard of the group searches the slice, rows are exchanged and merged inside the search kernel on the
+    group's first rank (ShardTail) and the merged rows are stored straight into EVERY rank's result block.  R = 1
+    is the pure row sharding of SURVEY.md section 8e (datasets larger than one GPU); R = world is pure replication
+    (an index that fits one GPU many times over: no query is answered twice, no per-shard top-k is wasted)."""
+
+    def __init__(self, local, n_total, rank, world, group=None, peer_exchange=True, replicas=1):
+        if world % replicas:
+            raise ValueError("replicas must divide the number of ranks")
         self.local, self.n_total, self.rank, self.world, self.group = local, int(n_total), rank, world, group
-        self.offsets = shard_offsets(n_total, world)
+        self.R, self.S = replicas, world // replicas
+        self.shard, self.replica = rank % self.S, rank // self.S
+        self.offsets = shard_offsets(n_total, self.S)
         self._buf = {}
-        self.peer_exchange = peer_exchange and world > 1     # False: packed NCCL all-gather
-        self.exchange = "none" if world == 1 else None       # set on first use: "peer-store" | "nccl-all-gather"
+        self.peer_exchange = peer_exchange and world > 1     # False: packed NCCL all-gather (pure sharding only)
+        self.exchange = "none" if world == 1 else None       # set on first use
         self._step = 0
 
     @staticmethod
+    def rows_of(n_total, rank, world, replicas=1):
+        """Rows [lo, hi) this rank indexes."""
+        S = world // replicas
+        return shard_range(n_total, rank % S, S)
+
+    @staticmethod
     def build(distance, local_rows, n_total, *, num_connections, num_nodes_search_construction, rank=0, world=1,
-              group=None, levels=None, seed=0, device=0, params=None):
+              group=None, levels=None, seed=0, device=0, params=None, replicas=1):
         """Ohnsw.build_batch_bigarray on this rank's rows."""
         local_rows = capi.as_mat(local_rows)
-        lo, hi = shard_range(n_total, rank, world)
+        lo, hi = ShardedHgraph.rows_of(n_total, rank, world, replicas)
         if local_rows.shape[0] != hi - lo:
             raise ValueError(f"rank {rank}: expected rows [{lo}, {hi}) of the dataset, got {local_rows.shape[0]} rows")
-        h = ohnsw.Hgraph(local_rows.shape[1], distance, num_connections, num_nodes_search_construction, seed + rank, device)
+        S = world // replicas
+        h = ohnsw.Hgraph(local_rows.shape[1], distance, num_connections, num_nodes_search_construction, seed + rank % S, device)
         for name, v in (params or {}).items():
             h.set_param(name, v)
         lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
         capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(local_rows), local_rows.shape[0], capi.ptr(lv)))
-        return ShardedHgraph(h, n_total, rank, world, group)
+        return ShardedHgraph(h, n_total, rank, world, group, replicas=replicas)
+
+    def query_slice(self, nq, replica=None):
+        """Queries [lo, hi) of a batch that replica group `replica` (default: this rank's) answers."""
+        return shard_range(nq, self.replica if replica is None else replica, self.R)
 
     def _peer_buffers(self, nq, k, dev):
         """Two symmetric-memory blocks (double buffered: the rows a call returns stay valid until the call after
-        next).  Layout in int32 words: gather rows [world][2][nq][k] | merged rows [2][nq][k] | arrival counters [nq].
-        Only rank 0's gather rows and counters are used (the home rank); the merged rows are stored into every
-        rank's block by whichever warp arrives last for a query."""
+        next).  Layout in int32 words: gather rows [S][2 (ids | dists, each [slice][k])] | merged rows [2][nq][k] |
+        arrival counters [slice].  Gather rows and counters are used on the first rank of each replica group (its
+        home); the merged rows are stored into every rank's block by whichever warp arrives last for a query."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = self.group if self.group is not None else dist.group.WORLD
         out = []
         nqk = nq * k
-        words = self.world * 2 * nqk + 2 * nqk + nq
+        sl_max = -(-nq // self.R)
+        lo, hi = self.query_slice(nq)
+        sl = hi - lo
+        g_words = self.S * 2 * sl_max * k
+        words = g_words + 2 * nqk + sl_max
         for _ in range(2):
             t = symm_mem.empty((words,), dtype=torch.int32, device=dev)
             t.zero_()
             hdl = symm_mem.rendezvous(t, group)
-            home = int(hdl.buffer_ptrs[0])
-            fin = self.world * 2 * nqk * 4
-            f_ids = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + fin for r in range(self.world)])
-            f_d = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + fin + nqk * 4 for r in range(self.world)])
-            out.append(dict(t=t, hdl=hdl, g_ids=home, g_d=home + self.world * nqk * 4, arrive=home + fin + 2 * nqk * 4,
-                            f_ids=f_ids, f_d=f_d, out_ids=t[self.world * 2 * nqk:self.world * 2 * nqk + nqk].view(nq, k),
-                            out_d=t[self.world * 2 * nqk + nqk:self.world * 2 * nqk + 2 * nqk].view(torch.float32).view(nq, k),
-                            arrive_t=t[self.world * 2 * nqk + 2 * nqk:]))
+            home = int(hdl.buffer_ptrs[self.replica * self.S])
+            fin = g_words * 4
+            # every rank's merged-row block, at this group's slice of the batch
+            f_ids = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + fin + lo * k * 4 for r in range(self.world)])
+            f_d = (C.c_void_p * self.world)(*[int(hdl.buffer_ptrs[r]) + fin + nqk * 4 + lo * k * 4 for r in range(self.world)])
+            out.append(dict(t=t, hdl=hdl, g_ids=home, g_d=home + self.S * sl * k * 4, arrive=home + fin + 2 * nqk * 4,
+                            f_ids=f_ids, f_d=f_d, out_ids=t[g_words:g_words + nqk].view(nq, k),
+                            out_d=t[g_words + nqk:g_words + 2 * nqk].view(torch.float32).view(nq, k),
+                            arrive_t=t[g_words + 2 * nqk:]))
         torch.cuda.synchronize()
         out[0]["hdl"].barrier(channel=0)
         torch.cuda.synchronize()
@@ -176,14 +202,18 @@ class ShardedHgraph:
         if key not in self._buf:
             dev = torch.device("cuda", self.local.info().device)
             peer = None
+            layout = f"{self.S} row shard(s) x {self.R} replica(s)"
             if self.peer_exchange and self.world <= 8:
                 try:
                     peer = self._peer_buffers(nq, k, dev)
-                    self.exchange = "peer stores into the home rank's gather block + last-arriver merge, both inside the search kernel; one device barrier per step"
+                    self.exchange = (f"{layout}; rows stored into the group home's gather block over NVLink and merged by the last warp "
+                                     "to arrive, both inside the search kernel; one device barrier per step")
                 except Exception as e:                      # no symmetric memory on this system / build
-                    self.exchange = f"one packed NCCL all-gather, then the merge kernel (symmetric memory unavailable: {type(e).__name__})"
+                    self.exchange = f"{layout}; one packed NCCL all-gather, then the merge kernel (symmetric memory unavailable: {type(e).__name__})"
             elif self.world > 1:
-                self.exchange = "one packed NCCL all-gather, then the merge kernel"
+                self.exchange = f"{layout}; one packed NCCL all-gather, then the merge kernel"
+            if peer is None and self.R > 1:
+                raise capi.HnswB200Error("replica groups need torch symmetric memory (peer-mapped buffers)")
             self._peer = peer
             # one packed block per rank: [0] = ids (int32), [1] = distances (fp32 bits) -> ONE all-gather
             packed = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
@@ -194,12 +224,13 @@ class ShardedHgraph:
                 out_d=torch.empty((nq, k), dtype=torch.float32, device=dev))}
         return self._buf[key]
 
-    def knn_batch_device(self, q_dev, *, k, ef=None, mode=capi.MODE_PARITY):
-        """Queries already on this rank's GPU (torch float32 [nq][dim], the same on every rank) ->
-        (ids int32 [nq][k] global, distances float32 [nq][k]) torch tensors on the GPU, on every rank.
-        Everything is enqueued on torch's current stream."""
+    def knn_batch_device(self, q_dev, *, k, ef=None, mode=capi.MODE_PARITY, nq=None):
+        """Queries on this rank's GPU -> (ids int32 [nq][k] global, distances float32 [nq][k]) torch tensors on the
+        GPU, on every rank.  `q_dev` is the whole batch (float32 [nq][dim], the same on every rank) or, with `nq`
+        given, only this rank's slice of it (`query_slice(nq)`).  Everything is enqueued on torch's current stream."""
         import torch
-        nq = q_dev.shape[0]
+        sliced = nq is not None
+        nq = q_dev.shape[0] if nq is None else nq
         b = self._buffers(nq, k)
         # torch's default stream has handle 0, which the C ABI reads as "the index's own stream, synchronous":
         # name the legacy default stream explicitly (cudaStreamLegacy = 1) so the call only enqueues, in order
@@ -211,15 +242,18 @@ class ShardedHgraph:
             return b["ids"], b["d"]
         import torch.distributed as dist
         if self._peer is not None:
-            # fused exchange + merge (ShardTail): rows go to rank 0's gather block, the last warp to arrive for a
-            # query merges and stores the global row into every rank's block; the barrier ends the step
+            # fused exchange + merge (ShardTail): rows go to the group home's gather block, the last warp to arrive for
+            # a query merges and stores the global row into every rank's block; the barrier ends the step
             pb, nxt = self._peer[self._step & 1], self._peer[(self._step + 1) & 1]
             self._step += 1
-            if self.rank == 0:
+            if self.shard == 0:
                 nxt["arrive_t"].zero_()            # counters of the NEXT call; ordered before this call's barrier
-            capi.check(capi.lib().hnswb200_search_device_sharded(
-                self.local._h, q_dev.data_ptr(), nq, k, k if ef is None else ef, mode, self.rank, self.world,
-                int(self.offsets[self.rank]), pb["g_ids"], pb["g_d"], pb["arrive"], self.world, pb["f_ids"], pb["f_d"], stream))
+            lo, hi = self.query_slice(nq)
+            q_ptr = q_dev.data_ptr() + (0 if sliced else lo * q_dev.shape[1] * 4)
+            if hi > lo:
+                capi.check(capi.lib().hnswb200_search_device_sharded(
+                    self.local._h, q_ptr, hi - lo, k, k if ef is None else ef, mode, self.shard, self.S,
+                    int(self.offsets[self.shard]), pb["g_ids"], pb["g_d"], pb["arrive"], self.world, pb["f_ids"], pb["f_d"], stream))
             pb["hdl"].barrier(channel=0)
             return pb["out_ids"], pb["out_d"]
         else:
@@ -233,15 +267,21 @@ class ShardedHgraph:
         return b["out_ids"], b["out_d"]
 
     def knn_batch_bigarray(self, batch, *, k, ef=None, mode=capi.MODE_PARITY, out=None):
-        """Ohnsw.knn_batch_bigarray with host buffers: H2D of the queries, per-shard search,
-        all-gather + merge, D2H of the merged rows."""
+        """Ohnsw.knn_batch_bigarray with host buffers: H2D of the queries this rank's group answers, search with the
+        fused exchange + merge, D2H of the merged rows."""
         import torch
         batch = capi.as_mat(batch, self.local.dim)
         if self.world == 1:
             return ohnsw.knn_batch_bigarray(self.local, batch, k=k, ef=ef, mode=mode, out=out)
         dev = torch.device("cuda", self.local.info().device)
-        q_dev = torch.from_numpy(batch).to(dev, non_blocking=True)
-        ids, d = self.knn_batch_device(q_dev, k=k, ef=ef, mode=mode)
+        nq = batch.shape[0]
+        if self._buffers(nq, k) and self._peer is not None:
+            lo, hi = self.query_slice(nq)
+            q_dev = torch.from_numpy(batch[lo:hi]).to(dev, non_blocking=True)     # only the slice travels
+            ids, d = self.knn_batch_device(q_dev, k=k, ef=ef, mode=mode, nq=nq)
+        else:
+            q_dev = torch.from_numpy(batch).to(dev, non_blocking=True)
+            ids, d = self.knn_batch_device(q_dev, k=k, ef=ef, mode=mode)
         if out is None:
             return ids.cpu().numpy(), d.cpu().numpy()
         torch.from_numpy(out[0]).copy_(ids, non_blocking=True)
