@@ -62,6 +62,10 @@ def parse():
     ap.add_argument("--metric", default="l2", choices=["l2", "angular"],
                     help="angular = SURVEY.md config C3 (GloVe shape): unit-norm Gaussian-mixture vectors, distance 1 - a.b")
     ap.add_argument("--latent", type=int, default=16, help="latent dimension of the SIFT-like generator")
+    ap.add_argument("--replicas", type=int, default=0,
+                    help="N > 1: the GPUs form S row shards x R replicas (S * R = N).  0 = automatic: R = N when one GPU holds the "
+                         "whole index (every config but c5), so each GPU answers 1/N of the queries on the full graph; R = 1 = "
+                         "pure row sharding (config c5, or an index larger than one GPU)")
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
                     help="a BASELINE.json configuration by name (SURVEY.md section 8d); sets rows/dim/nq/M/metric/latent")
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE",
@@ -81,7 +85,7 @@ CONFIGS = {
     "c2": dict(n=1_000_000, dim=128, nq=10_000, M=16, efc=200, metric="l2", latent=16),
     "c3": dict(n=1_183_514, dim=100, nq=10_000, M=24, efc=200, metric="angular"),
     "c4": dict(n=1_000_000, dim=960, nq=1_000, M=16, efc=200, metric="l2", latent=32),
-    "c5": dict(n=10_000_000, dim=96, nq=10_000, M=16, efc=200, metric="l2", latent=16),
+    "c5": dict(n=10_000_000, dim=96, nq=10_000, M=16, efc=200, metric="l2", latent=16, replicas=1),
 }
 
 
@@ -320,8 +324,14 @@ def run_ours(a):
     # Timing rule: inputs larger than L2, or an L2 flush between timed iterations.  One shard's index is
     # rows x (vector + layer-0 list) bytes; when that is not well above the L2 size (small --rows, or 1M rows cut
     # into 8 shards) every step is preceded by a write of 2 x L2 bytes and timed on its own.
+    # layout of the N GPUs: S row shards x R replicas (ocaml-hnsw_b200/sharded.py)
+    full_bytes = a.n * (a.dim * 4 + 2 * a.M * 4)
+    R = a.replicas if a.replicas > 0 else (world if full_bytes <= 64 * 2**30 else 1)
+    if world % R:
+        raise SystemExit("--replicas must divide --gpus")
+    S = world // R
     l2_bytes = int(torch.cuda.get_device_properties(dev).L2_cache_size)
-    index_bytes = (a.n // world) * (a.dim * 4 + 2 * a.M * 4)
+    index_bytes = (a.n // S) * (a.dim * 4 + 2 * a.M * 4)
     flush = index_bytes <= 2 * l2_bytes
     flush_buf = torch.empty(2 * l2_bytes, dtype=torch.uint8, device=dev) if flush else None
 
@@ -330,17 +340,17 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     # ---- synthetic inputs (every rank generates the same arrays, then keeps its rows)
-    lo, hi = shard_range(a.n, rank, world)
+    lo, hi = ShardedHgraph.rows_of(a.n, rank, world, R)
     X = make_data(a, a.n, 1234)[lo:hi].copy()
     Q = make_data(a, a.nq, 4321)
     metric = Ohnsw.distance_l2 if a.metric == "l2" else Ohnsw.distance_angular
-    lv = draw_levels(hi - lo, a.M, 7 + rank)
+    lv = draw_levels(hi - lo, a.M, 7 + rank % S)           # replicas of a shard draw the same levels: identical graphs
 
     # ---- index build (outside the timed search region; reported as build seconds)
     barrier()
     t0 = time.perf_counter()
     sh = ShardedHgraph.build(metric, X, a.n, num_connections=a.M, num_nodes_search_construction=a.efc,
-                             rank=rank, world=world, levels=lv, device=local_rank, params=a.params)
+                             rank=rank, world=world, levels=lv, device=local_rank, params=a.params, replicas=R)
     torch.cuda.synchronize()
     build_s = max_over_ranks(time.perf_counter() - t0)
     h = sh.local
@@ -355,7 +365,8 @@ def run_ours(a):
         gd = gather_rows(torch.from_numpy(gt_d_l).to(dev), world)
         go_i = torch.empty((a.nq, a.k), dtype=torch.int32, device=dev)
         go_d = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
-        capi.check(capi.lib().hnswb200_merge_topk_device(gi.data_ptr(), gd.data_ptr(), world, a.nq, a.k, 0,
+        # ranks 0 .. S-1 are one replica group: their shards cover the dataset once
+        capi.check(capi.lib().hnswb200_merge_topk_device(gi.data_ptr(), gd.data_ptr(), S, a.nq, a.k, 0,
                                                          capi.ptr(sh.offsets), go_i.data_ptr(), go_d.data_ptr(), None))
         gt_ids, gt_d = go_i.cpu().numpy(), go_d.cpu().numpy()
     else:
@@ -439,10 +450,12 @@ def run_ours(a):
     r_ids = torch.empty((a.nq, a.k), dtype=torch.int32, device=dev)
     r_d = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
+    q_lo, q_hi = sh.query_slice(a.nq)                  # the queries this rank's launch of a step covers (all of them when R = 1)
+    nq_launch = q_hi - q_lo
     for i in range(max(3, min(a.steps, 10))):
         if flush:
             flush_l2(i)
-        h.search_device(q_dev.data_ptr(), a.nq, a.k, ef_star, r_ids.data_ptr(), r_d.data_ptr())   # library stream: its events bracket the one kernel
+        h.search_device(q_dev.data_ptr() + q_lo * a.dim * 4, nq_launch, a.k, ef_star, r_ids.data_ptr(), r_d.data_ptr())   # library stream: its events bracket the one kernel
         st = h.stats()
         kms.append(st.search_kernel_ms)
         abytes = st.search_algorithmic_bytes          # counted: n_dist*4*dim + rows*4*slots + nq*(4*dim + 8*k)
@@ -523,13 +536,71 @@ def run_ours(a):
                          f"queries, ef={ef_star}, {threads} threads; single thread {2000 / one:.0f} queries/s on 2000 queries; "
                          f"ids identical to the GPU's: {same}"}
 
+    # ---- the other layout beside it (N > 1, automatic layout chose replicas): pure row sharding, device-timed only
+    alt = None
+    exchange_desc = sh.exchange
+    if world > 1 and R > 1 and a.replicas == 0:
+        del sh, h
+        lo2, hi2 = ShardedHgraph.rows_of(a.n, rank, world, 1)
+        X2 = make_data(a, a.n, 1234)[lo2:hi2].copy()
+        barrier()
+        t0 = time.perf_counter()
+        sh2 = ShardedHgraph.build(metric, X2, a.n, num_connections=a.M, num_nodes_search_construction=a.efc, rank=rank, world=world,
+                                  levels=draw_levels(hi2 - lo2, a.M, 7 + rank), device=local_rank, params=a.params, replicas=1)
+        torch.cuda.synchronize()
+        build2_s = max_over_ranks(time.perf_counter() - t0)
+
+        def rec2(ef):
+            with torch.cuda.stream(stream):
+                ids2, _ = sh2.knn_batch_device(q_dev, k=a.k, ef=ef)
+            stream.synchronize()
+            return H.Recall.ids(gt_ids, ids2.cpu().numpy())
+        lo_ef, hi_ef = a.k - 1, None
+        for ef in EF_SWEEP:
+            if ef >= a.k:
+                if rec2(ef) >= a.target_recall:
+                    hi_ef = ef
+                    break
+                lo_ef = ef
+        if hi_ef is not None:
+            while hi_ef - lo_ef > 1:
+                mid = (lo_ef + hi_ef) // 2
+                if rec2(mid) >= a.target_recall:
+                    hi_ef = mid
+                else:
+                    lo_ef = mid
+            rec_alt = rec2(hi_ef)
+            flush2 = (a.n // world) * (a.dim * 4 + 2 * a.M * 4) <= 2 * l2_bytes
+            if flush2 and flush_buf is None:
+                flush_buf = torch.empty(2 * l2_bytes, dtype=torch.uint8, device=dev)
+            evs = []
+            for i in range(a.steps):
+                if flush2:
+                    flush_l2(i)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record()
+                    sh2.knn_batch_device(q_dev, k=a.k, ef=hi_ef)
+                    e1.record()
+                evs.append((e0, e1))
+            stream.synchronize()
+            barrier()
+            ms2 = sum_of_step_max([e0.elapsed_time(e1) for e0, e1 in evs])
+            alt = {"layout": {"row_shards": world, "replicas": 1}, "value": a.nq * a.steps / (ms2 * 1e-3), "unit": "queries/s",
+                   "ms_per_step": ms2 / a.steps, "ef": hi_ef, "recall_at_10": round(rec_alt, 4), "build_seconds": build2_s,
+                   "l2": "L2 flushed before every step" if flush2 else "no flush (shard index larger than 2 x L2)",
+                   "note": "SURVEY.md 8e's pure row sharding on the same run: every GPU answers every query on 1/N of the rows; what "
+                           "a dataset larger than one GPU needs, not the faster layout for one that fits"}
+
     if rank == 0:
         line = {
             "metric": "QPS @ recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef_star, "recall_at_10": round(rec_star, 4), "mode": "parity",
-                       "sharding": (f"{world} row shards, one process per GPU; exchange: {sh.exchange}" if world > 1 else "single index"),
+                       "sharding": (f"one process per GPU; {exchange_desc}" if world > 1 else "single index"),
+                       "layout": {"row_shards": S, "replicas": R, "queries_per_gpu_per_step": nq_launch, "rows_per_gpu": hi - lo},
                        "l2": (f"shard index {index_bytes / 1e6:.0f} MB vs {l2_bytes / 1e6:.0f} MB of L2: "
                               + ("L2 flushed (write of 2 x L2 bytes) before every step, steps timed one by one" if flush
                                  else "inputs larger than L2, no flush between steps")),
@@ -551,9 +622,11 @@ def run_ours(a):
                          "note": ("shard index fits L2: within a step most of the algorithmic bytes are served from L2, so "
                                   "frac against the HBM peak is not a DRAM figure here") if flush else None,
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
-                         "dist_evals_per_query": st.search_n_dist / a.nq, "expansions_per_query": st.search_n_exp0 / a.nq,
+                         "queries_per_launch": nq_launch,
+                         "dist_evals_per_query": st.search_n_dist / nq_launch, "expansions_per_query": st.search_n_exp0 / nq_launch,
                          "visited_spills": int(st.search_visited_overflows)},
             "cpu_baseline": cpu,
+            "row_sharded": alt,
             "clocks": clocks,
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)

@@ -94,3 +94,32 @@ def test_sharded_build_rejects_wrong_rows():
     with pytest.raises(ValueError, match="expected rows"):
         ShardedHgraph.build(0, np.zeros((10, 4), np.float32), 100, num_connections=4, num_nodes_search_construction=10,
                             rank=0, world=2)
+
+
+def test_shards_times_replicas_partition():
+    """S row shards x R replicas (sharded.py): every replica group covers the rows exactly once, the replica groups
+    cover the queries exactly once, and the first rank of a group is its home."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from ocaml_hnsw_b200.sharded import ShardedHgraph, shard_range
+
+    class FakeLocal:
+        pass
+    for world in (1, 2, 4, 8):
+        for R in (r for r in (1, 2, 4, 8) if world % r == 0):
+            S = world // R
+            n, nq = 1001, 37
+            rows = [ShardedHgraph.rows_of(n, r, world, R) for r in range(world)]
+            for g in range(R):
+                group = rows[g * S:(g + 1) * S]
+                assert group[0][0] == 0 and group[-1][1] == n and all(a[1] == b[0] for a, b in zip(group, group[1:]))
+                assert group == rows[:S]                                 # every group holds the same shards
+            hs = [ShardedHgraph(FakeLocal(), n, r, world, replicas=R) for r in range(world)]
+            slices = sorted({h.query_slice(nq) for h in hs})
+            assert slices[0][0] == 0 and slices[-1][1] == nq and all(a[1] == b[0] for a, b in zip(slices, slices[1:]))
+            assert len(slices) == R
+            for r, h in enumerate(hs):
+                assert (h.shard, h.replica) == (r % S, r // S) and h.query_slice(nq) == shard_range(nq, r // S, R)
+                assert len(h.offsets) == S and h.offsets[h.shard] == rows[r][0]
+    with pytest.raises(ValueError):
+        ShardedHgraph(FakeLocal(), 10, 0, 4, replicas=3)
