@@ -47,20 +47,34 @@ void launch_bruteforce(const float* d_data, int64_t n, const float* d_q, int64_t
 int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, int64_t nq, int ld, int dim, int k,
                              int num_sms, int32_t* d_ids, float* d_dists, cudaStream_t s, uint64_t* launches) {
   const int kp = round_up(dim, hb::TC_KC);
+  // round 2: operands pre-tiled for bulk copies + the warp-specialised kernel (bruteforce_tc2.cuh);
+  // HNSWB200_BRUTEFORCE=tc1 keeps the round-1 kernel (cp.async by every thread) for comparison
+  const char* which = std::getenv("HNSWB200_BRUTEFORCE");
+  const bool tc2 = !(which && std::string(which) == "tc1");
+  const int64_t n_pad = (n + hb::TC_N - 1) / hb::TC_N * hb::TC_N, nq_pad = (nq + hb::TC_M - 1) / hb::TC_M * hb::TC_M;
   DevBuf<__nv_bfloat16> x_hi, x_lo, q_hi, q_lo;
   DevBuf<float> x_norm, scal, bound;
   DevBuf<int> flags;
   DevBuf<unsigned int> gthr;
   DevBuf<uint64_t> partial;
-  x_hi.reserve((size_t)n * kp); x_lo.reserve((size_t)n * kp); q_hi.reserve((size_t)nq * kp); q_lo.reserve((size_t)nq * kp);
+  x_hi.reserve((size_t)n_pad * kp); x_lo.reserve((size_t)n_pad * kp); q_hi.reserve((size_t)nq_pad * kp); q_lo.reserve((size_t)nq_pad * kp);
   x_norm.reserve((size_t)n); scal.reserve(4); flags.reserve((size_t)nq + 4);
   CUDA_CHECK(cudaMemsetAsync(scal.p, 0, 4 * sizeof(float), s));     // [0] max ||x||^2, [1] any lo (int), [2] max ||q||^2 (unused)
   int wpb = 8;
   EvTimer tm(s);
-  hb::bf16_split_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_data, ld, dim, n, kp, x_hi.p, x_lo.p, x_norm.p,
-                                                                            reinterpret_cast<int*>(scal.p + 1), scal.p);
-  hb::bf16_split_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_q, ld, dim, nq, kp, q_hi.p, q_lo.p, nullptr,
-                                                                             reinterpret_cast<int*>(scal.p + 1), scal.p + 2);
+  if (tc2) {
+    for (DevBuf<__nv_bfloat16>* b : {&x_hi, &x_lo}) CUDA_CHECK(cudaMemsetAsync(b->p, 0, (size_t)n_pad * kp * 2, s));
+    for (DevBuf<__nv_bfloat16>* b : {&q_hi, &q_lo}) CUDA_CHECK(cudaMemsetAsync(b->p, 0, (size_t)nq_pad * kp * 2, s));
+    hb::bf16_tile_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_data, ld, dim, n, kp, hb::TC_N, x_hi.p, x_lo.p, x_norm.p,
+                                                                             reinterpret_cast<int*>(scal.p + 1), scal.p);
+    hb::bf16_tile_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_q, ld, dim, nq, kp, hb::TC_M, q_hi.p, q_lo.p, nullptr,
+                                                                              reinterpret_cast<int*>(scal.p + 1), scal.p + 2);
+  } else {
+    hb::bf16_split_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_data, ld, dim, n, kp, x_hi.p, x_lo.p, x_norm.p,
+                                                                              reinterpret_cast<int*>(scal.p + 1), scal.p);
+    hb::bf16_split_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, s>>>(d_q, ld, dim, nq, kp, q_hi.p, q_lo.p, nullptr,
+                                                                               reinterpret_cast<int*>(scal.p + 1), scal.p + 2);
+  }
   CUDA_CHECK(cudaGetLastError());
   tm.lap("bf16_split_kernel x2");
   float h_scal[4];
@@ -79,12 +93,18 @@ int64_t launch_bruteforce_tc(const float* d_data, int64_t n, const float* d_q, i
   hb::TcParams p{};
   p.x_hi = x_hi.p; p.x_lo = x_lo.p; p.q_hi = q_hi.p; p.q_lo = q_lo.p; p.x_norm = x_norm.p;
   p.n = n; p.nq = nq; p.kp = kp; p.segs = any_lo ? 3 : 1; p.split_len = split_len; p.partial = partial.p; p.bound = bound.p; p.gthr = gthr.p;
-  size_t smem = hb::tc_smem_bytes();
-  CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tm.lap("(sync, alloc)");
-  hb::bruteforce_tc_kernel<<<dim3(qblocks, splits), hb::TC_THREADS, smem, s>>>(p);
+  if (tc2) {
+    size_t smem = hb::tc2_smem_bytes();
+    CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hb::bruteforce_tc2_kernel<<<dim3(qblocks, splits), hb::T2_THREADS, smem, s>>>(p);
+  } else {
+    size_t smem = hb::tc_smem_bytes();
+    CUDA_CHECK(cudaFuncSetAttribute(hb::bruteforce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hb::bruteforce_tc_kernel<<<dim3(qblocks, splits), hb::TC_THREADS, smem, s>>>(p);
+  }
   CUDA_CHECK(cudaGetLastError());
-  tm.lap(p.segs == 3 ? "bruteforce_tc_kernel (3 segments)" : "bruteforce_tc_kernel (1 segment)");
+  tm.lap(p.segs == 3 ? "bruteforce_tc kernel (3 segments)" : "bruteforce_tc kernel (1 segment)");
 
   hb::TcFinishParams f{};
   f.g.vec = d_data; f.g.ld4 = ld / 4; f.g.chunks = ld / 4; f.g.metric = 0; f.g.n = (int)n;

@@ -20,6 +20,7 @@
 #include "build.cuh"
 #include "bruteforce.cuh"
 #include "bruteforce_tc.cuh"
+#include "bruteforce_tc2.cuh"
 #include "merge.cuh"
 #include "stats.cuh"
 
