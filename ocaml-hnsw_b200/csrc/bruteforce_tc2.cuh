@@ -28,9 +28,12 @@ constexpr int T2_EPI_WARPS = 8;
 constexpr int T2_THREADS = (2 + T2_EPI_WARPS) * 32;
 constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
 constexpr uint32_t T2_TMEM_COLS = 512;
+constexpr int T2_LIST_LD = TC_KP + 1;        // one sorted list per thread, odd stride (bank spread)
+constexpr int T2_DD_LD = 33;                 // 32 distances of the block being examined, per thread, odd stride
 
 __host__ __device__ inline size_t tc2_smem_bytes() {
-  return (size_t)T2_STAGES * TC_STAGE_BYTES + (size_t)T2_EPI_THREADS * TC_LIST_LD * 8 + 2 * TC_N * 4 + 16 * 8 + 64;
+  return (size_t)T2_STAGES * TC_STAGE_BYTES + (size_t)T2_EPI_THREADS * T2_LIST_LD * 8 + (size_t)T2_EPI_THREADS * T2_DD_LD * 4 +
+         (size_t)T2_EPI_WARPS * 2 * (TC_N / 2) * 4 + 16 * 8 + 64;
 }
 
 // fp32 rows -> bf16 hi / lo in TILED order: tile T = row / RT, k-chunk kc = c / 64; inside the (RT x 64) block the
@@ -98,8 +101,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
   extern __shared__ __align__(128) unsigned char tc_smem[];
   unsigned char* stages = tc_smem;
   uint64_t* lists = reinterpret_cast<uint64_t*>(tc_smem + T2_STAGES * TC_STAGE_BYTES);
-  float* xn = reinterpret_cast<float*>(lists + T2_EPI_THREADS * TC_LIST_LD);            // [2][TC_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xn + 2 * TC_N);
+  float* dds = reinterpret_cast<float*>(lists + T2_EPI_THREADS * T2_LIST_LD);           // [thread][T2_DD_LD]
+  float* xn = dds + T2_EPI_THREADS * T2_DD_LD;                                          // [epilogue warp][2][TC_N / 2]: each warp's own copy
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xn + T2_EPI_WARPS * 2 * (TC_N / 2));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   // bars: [0..2] full (stage landed), [3..5] empty (stage read by the MMAs), [6..7] acc_full, [8..9] acc_empty
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + T2_STAGES), bar_accf = smem_u32(bars + 2 * T2_STAGES),
@@ -179,35 +183,47 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
     const int et = tid - 64;                                   // 0..255
     const int quarter = warp & 3, half = (warp - 2) >> 2;      // TMEM lanes 32 * quarter .., columns 128 * half ..
     const int row = quarter * 32 + lane;
-    uint64_t* my_list = lists + (size_t)et * TC_LIST_LD;
-    uint64_t* my_stage = my_list + TC_KP;
+    uint64_t* my_list = lists + (size_t)et * T2_LIST_LD;
+    float* my_dd = dds + (size_t)et * T2_DD_LD;
     int cnt = 0;
     float thr = __int_as_float(0x7f800000);
     const bool live = q0 + row < p.nq;
+    // Nothing in a tile's epilogue waits for another warp or for a global round trip: the 128 column norms a
+    // warp needs are its own shared copy (one coalesced load, four per lane, under the wait for the accumulator),
+    // the query's shared threshold is read one tile ahead, and its updates are fire-and-forget reductions.
+    unsigned int gthr_next = 0xffffffffu;
     for (int64_t tile = 0; tile < ntiles; tile++) {
       const int a = (int)(tile & 1);
       const int64_t xb = x_begin + tile * TC_N;
-      mbar_wait(bar_accf + 8 * a, (uint32_t)((tile >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // (every epilogue thread has left tile - 2 by now: the MMAs of this tile waited for acc_empty)
-      float* xna = xn + a * TC_N;
-      xna[et] = xb + et < x_end ? p.x_norm[xb + et] : __int_as_float(0x7f800000);
-      if (live) thr = fminf(thr, ord2f(__ldcg(p.gthr + q0 + row)));
-      asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-      int ns = 0;
-      auto flush = [&]() {
-        for (int e = 0; e < ns; e++) {
-          const uint64_t key = my_stage[e];
-          if (cnt == TC_KP && key >= my_list[TC_KP - 1]) continue;
-          int pos = cnt < TC_KP ? cnt : TC_KP - 1;
-          while (pos > 0 && my_list[pos - 1] > key) { my_list[pos] = my_list[pos - 1]; pos--; }
-          my_list[pos] = key;
-          if (cnt < TC_KP) cnt++;
-        }
-        ns = 0;
+      float* xna = xn + ((size_t)(warp - 2) * 2 + a) * (TC_N / 2) - half * (TC_N / 2);   // indexed by the tile's column like before
+      {
+        const int64_t c0 = xb + half * (TC_N / 2) + lane * 4;
+        float4 nv;
+        nv.x = c0 + 0 < x_end ? __ldg(p.x_norm + c0 + 0) : __int_as_float(0x7f800000);
+        nv.y = c0 + 1 < x_end ? __ldg(p.x_norm + c0 + 1) : __int_as_float(0x7f800000);
+        nv.z = c0 + 2 < x_end ? __ldg(p.x_norm + c0 + 2) : __int_as_float(0x7f800000);
+        nv.w = c0 + 3 < x_end ? __ldg(p.x_norm + c0 + 3) : __int_as_float(0x7f800000);
+        thr = fminf(thr, ord2f(gthr_next));
+        if (live) gthr_next = __ldcg(p.gthr + q0 + row);                 // consumed at the next tile
+        mbar_wait(bar_accf + 8 * a, (uint32_t)((tile >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        reinterpret_cast<float4*>(xna + half * (TC_N / 2))[lane] = nv;      // (this warp read the previous contents two tiles ago)
+        __syncwarp();
+      }
+      // A value below the row's threshold enters the sorted list of the TC_KP best at once (ONE copy of this code:
+      // the 32-fold unrolled scan only records which columns qualify).
+      auto insert = [&](uint64_t key) {
+        if (cnt == TC_KP && key >= my_list[TC_KP - 1]) return;
+        int pos = cnt < TC_KP ? cnt : TC_KP - 1;
+        while (pos > 0 && my_list[pos - 1] > key) { my_list[pos] = my_list[pos - 1]; pos--; }
+        my_list[pos] = key;
+        if (cnt < TC_KP) cnt++;
         if (cnt == TC_KP) {
           const float t16 = key_dist(my_list[TC_KP - 1]);
-          if (t16 < thr) { thr = t16; if (live) atomicMin(p.gthr + q0 + row, f2ord(t16)); }
+          if (t16 < thr) {
+            thr = t16;
+            if (live) asm volatile("red.global.min.u32 [%0], %1;" ::"l"(p.gthr + q0 + row), "r"(f2ord(t16)) : "memory");
+          }
         }
       };
       auto scan = [&](uint32_t (&r)[32], int cb) {
@@ -222,14 +238,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
           m2.x = fminf(m2.x, fminf(d0.x, d1.x));
           m2.y = fminf(m2.y, fminf(d0.y, d1.y));
         }
-        if (fminf(m2.x, m2.y) < thr) {                                         // rare after the first tiles
+        if (fminf(m2.x, m2.y) < thr) {                                         // some column of this block qualifies
+          unsigned mask = 0;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             const float dd = fmaf(-2.f, __uint_as_float(r[j]), xna[cb * 32 + j]);
-            if (dd < thr) {
-              my_stage[ns++] = make_key(dd, (uint32_t)(xb + cb * 32 + j));
-              if (ns == TC_STAGE_CAP) flush();
-            }
+            my_dd[j] = dd;
+            mask |= dd < thr ? (1u << j) : 0u;
+          }
+#pragma unroll 1
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float dd = my_dd[j];
+            if (dd < thr) insert(make_key(dd, (uint32_t)(xb + cb * 32 + j)));
           }
         }
       };
@@ -245,7 +267,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
         if (cb + 2 < TC_N / 2 / 32) tmem_ld32_async(tbase + (uint32_t)((cb + 2) * 32), ra);
         scan(rb, half * (TC_N / 2 / 32) + cb + 1);
       }
-      flush();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acce + 8 * a);                              // this thread no longer reads accumulator a (nor xn[a])
     }
