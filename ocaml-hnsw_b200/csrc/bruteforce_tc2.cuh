@@ -28,8 +28,9 @@ constexpr int T2_EPI_WARPS = 8;
 constexpr int T2_THREADS = (2 + T2_EPI_WARPS) * 32;
 constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
 constexpr uint32_t T2_TMEM_COLS = 512;
-constexpr int T2_LIST_LD = TC_KP + 1;        // one sorted list per thread, odd stride (bank spread)
-constexpr int T2_DD_LD = 33;                 // 32 distances of the block being examined, per thread, odd stride
+constexpr int T2_STAGE_CAP = 6;              // qualifying values a thread parks between two list updates
+constexpr int T2_LIST_LD = TC_KP + T2_STAGE_CAP + 1;   // sorted list + parked values per thread, odd stride (bank spread)
+constexpr int T2_DD_LD = 9;                  // the 8 distances of the column group being examined, per thread, odd stride
 
 __host__ __device__ inline size_t tc2_smem_bytes() {
   return (size_t)T2_STAGES * TC_STAGE_BYTES + (size_t)T2_EPI_THREADS * T2_LIST_LD * 8 + (size_t)T2_EPI_THREADS * T2_DD_LD * 4 +
@@ -185,13 +186,35 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
     const int row = quarter * 32 + lane;
     uint64_t* my_list = lists + (size_t)et * T2_LIST_LD;
     float* my_dd = dds + (size_t)et * T2_DD_LD;
-    int cnt = 0;
+    uint64_t* my_stage = my_list + TC_KP;
+    int cnt = 0, ns = 0;
     float thr = __int_as_float(0x7f800000);
     const bool live = q0 + row < p.nq;
     // Nothing in a tile's epilogue waits for another warp or for a global round trip: the 128 column norms a
     // warp needs are its own shared copy (one coalesced load, four per lane, under the wait for the accumulator),
     // the query's shared threshold is read one tile ahead, and its updates are fire-and-forget reductions.
-    unsigned int gthr_next = 0xffffffffu;
+    // A value below the row's threshold is first PARKED (one store); the sorted list of the TC_KP best is updated
+    // for all 32 rows of the warp together, when some row's parking space is nearly full and once at the end:
+    // an insertion is a serial, divergent loop, and a warp pays for the busiest of its rows each time it runs.
+    auto insert = [&](uint64_t key) {
+      if (cnt == TC_KP && key >= my_list[TC_KP - 1]) return;
+      int pos = cnt < TC_KP ? cnt : TC_KP - 1;
+      while (pos > 0 && my_list[pos - 1] > key) { my_list[pos] = my_list[pos - 1]; pos--; }
+      my_list[pos] = key;
+      if (cnt < TC_KP) cnt++;
+      if (cnt == TC_KP) {
+        const float t16 = key_dist(my_list[TC_KP - 1]);
+        if (t16 < thr) {
+          thr = t16;
+          if (live) asm volatile("red.global.min.u32 [%0], %1;" ::"l"(p.gthr + q0 + row), "r"(f2ord(t16)) : "memory");
+        }
+      }
+    };
+    auto flush = [&]() {
+      for (int e = 0; e < ns; e++) insert(my_stage[e]);
+      ns = 0;
+    };
+    unsigned int gthr_next = live ? __ldcg(p.gthr + q0 + row) : 0xffffffffu;     // what other splits of the query have reached so far
     for (int64_t tile = 0; tile < ntiles; tile++) {
       const int a = (int)(tile & 1);
       const int64_t xb = x_begin + tile * TC_N;
@@ -210,49 +233,44 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
         reinterpret_cast<float4*>(xna + half * (TC_N / 2))[lane] = nv;      // (this warp read the previous contents two tiles ago)
         __syncwarp();
       }
-      // A value below the row's threshold enters the sorted list of the TC_KP best at once (ONE copy of this code:
-      // the 32-fold unrolled scan only records which columns qualify).
-      auto insert = [&](uint64_t key) {
-        if (cnt == TC_KP && key >= my_list[TC_KP - 1]) return;
-        int pos = cnt < TC_KP ? cnt : TC_KP - 1;
-        while (pos > 0 && my_list[pos - 1] > key) { my_list[pos] = my_list[pos - 1]; pos--; }
-        my_list[pos] = key;
-        if (cnt < TC_KP) cnt++;
-        if (cnt == TC_KP) {
-          const float t16 = key_dist(my_list[TC_KP - 1]);
-          if (t16 < thr) {
-            thr = t16;
-            if (live) asm volatile("red.global.min.u32 [%0], %1;" ::"l"(p.gthr + q0 + row), "r"(f2ord(t16)) : "memory");
+      // the 8 columns 8u .. 8u+7 of a 32-column block (u is a literal at every call)
+      auto group = [&](uint32_t (&r)[32], int cb, int u) {
+        unsigned m8 = 0;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+          const float dd = fmaf(-2.f, __uint_as_float(r[8 * u + jj]), xna[cb * 32 + 8 * u + jj]);
+          my_dd[jj] = dd;
+          m8 |= dd < thr ? (1u << jj) : 0u;
+        }
+#pragma unroll 1
+        while (m8) {
+          const int jj = __ffs(m8) - 1;
+          m8 &= m8 - 1u;
+          const float dd = my_dd[jj];
+          if (dd < thr) {
+            const uint64_t key = make_key(dd, (uint32_t)(xb + cb * 32 + 8 * u + jj));
+            if (ns < T2_STAGE_CAP) my_stage[ns++] = key; else insert(key);
           }
         }
       };
       auto scan = [&](uint32_t (&r)[32], int cb) {
         const float4* xn4 = reinterpret_cast<const float4*>(xna + cb * 32);
-        float2 m2 = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
         const float2 neg2 = make_float2(-2.f, -2.f);
+        float g[4];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-          const float4 nv = xn4[j4];                                          // columns past the end carry +inf norms
-          const float2 d0 = fma2(neg2, make_float2(__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1])), make_float2(nv.x, nv.y));
-          const float2 d1 = fma2(neg2, make_float2(__uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])), make_float2(nv.z, nv.w));
-          m2.x = fminf(m2.x, fminf(d0.x, d1.x));
-          m2.y = fminf(m2.y, fminf(d0.y, d1.y));
+        for (int u = 0; u < 4; u++) {
+          const float4 n0 = xn4[2 * u], n1 = xn4[2 * u + 1];                  // columns past the end carry +inf norms
+          const float2 d0 = fma2(neg2, make_float2(__uint_as_float(r[8 * u + 0]), __uint_as_float(r[8 * u + 1])), make_float2(n0.x, n0.y));
+          const float2 d1 = fma2(neg2, make_float2(__uint_as_float(r[8 * u + 2]), __uint_as_float(r[8 * u + 3])), make_float2(n0.z, n0.w));
+          const float2 d2 = fma2(neg2, make_float2(__uint_as_float(r[8 * u + 4]), __uint_as_float(r[8 * u + 5])), make_float2(n1.x, n1.y));
+          const float2 d3 = fma2(neg2, make_float2(__uint_as_float(r[8 * u + 6]), __uint_as_float(r[8 * u + 7])), make_float2(n1.z, n1.w));
+          g[u] = fminf(fminf(fminf(d0.x, d0.y), fminf(d1.x, d1.y)), fminf(fminf(d2.x, d2.y), fminf(d3.x, d3.y)));
         }
-        if (fminf(m2.x, m2.y) < thr) {                                         // some column of this block qualifies
-          unsigned mask = 0;
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const float dd = fmaf(-2.f, __uint_as_float(r[j]), xna[cb * 32 + j]);
-            my_dd[j] = dd;
-            mask |= dd < thr ? (1u << j) : 0u;
-          }
-#pragma unroll 1
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            const float dd = my_dd[j];
-            if (dd < thr) insert(make_key(dd, (uint32_t)(xb + cb * 32 + j)));
-          }
+        if (fminf(fminf(g[0], g[1]), fminf(g[2], g[3])) < thr) {               // some column of this block qualifies
+          if (g[0] < thr) group(r, cb, 0);
+          if (g[1] < thr) group(r, cb, 1);
+          if (g[2] < thr) group(r, cb, 2);
+          if (g[3] < thr) group(r, cb, 3);
         }
       };
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TC_N + half * (TC_N / 2));
@@ -269,7 +287,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) bruteforce_tc2_kernel(const TcP
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_acce + 8 * a);                              // this thread no longer reads accumulator a (nor xn[a])
+      if (__any_sync(FULL, ns >= T2_STAGE_CAP - 1)) flush();
     }
+    flush();
     if (live) {
       const size_t slot = ((size_t)blockIdx.y * TC_HALVES + half) * p.nq + (q0 + row);
       uint64_t* out = p.partial + slot * TC_KP;
