@@ -60,7 +60,14 @@ extern "C" {
  * OHNSW   = lib/ohnsw.ml   (strict accept `d < top`, 2M links for a new node on layer 0,
  *                           -1/NaN padding)
  * HNSW_BA = lib/hnsw.ml + lib/hnsw_algo.ml `Hnsw.Ba` (ties accepted `d <= top`,
- *                           M links for a new node on every layer, +inf padding) */
+ *                           M links for a new node on every layer, small candidate sets kept whole,
+ *                           +inf padding).
+ * What HNSW_BA is NOT: an edge-for-edge restatement of path A's build.  It is path B's insert (pruning keyed
+ * on distances to the node being pruned, the paper's rule) run with path A's parameters.  Path A prunes a
+ * neighbour with distances to the INSERTED point (lib/hnsw_algo.ml:633-635,678-689), force-keeps candidates of
+ * degree <= 1 (`do_not_isolate`, :591-592), descends upper layers with a heap (:393-437) and orders its lists
+ * by pairing-heap / Base.Map fold order; none of that is pinned by a reference test and none is reproduced.
+ * Search on an imported path-A graph (id_base = 1) follows path A's acceptance rule exactly. */
 #define HNSWB200_FLAVOUR_OHNSW 0
 #define HNSWB200_FLAVOUR_HNSW_BA 1
 
@@ -128,8 +135,12 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
  * warps wait for the piece that holds their query; default: copy first, then search),
  * "stage_rows" (rows of >= 1 KB are gathered with cp.async.bulk into a per-warp shared-memory ring of
  * this many rows, 4..32; 0 = automatic, -1 = per-lane 128-bit loads instead),
+ * "stage_ahead" (rows beyond that ring sent for with a bulk L2 prefetch, 0..31; -1 = automatic),
+ * "hash_bits" (visited hash entries: 0 = automatic, 16 = quotiented 16-bit entries wherever the id range allows,
+ * 32 = plain ids), "gang" (warps working on one query / one insert when a batch is smaller than the GPU:
+ * 0 = automatic, 1 = never, 2 or 4),
  * "row_floats" (stride of a vector row in floats, a multiple of 4 >= dim; default dim rounded up to
- * 4; only on an empty index). */
+ * 4; only on an empty index).  None of them changes a result: only where data sits and who computes it. */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
 int hnswb200_destroy(hnswb200_index* idx);
 
