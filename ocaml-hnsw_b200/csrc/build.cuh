@@ -19,6 +19,13 @@
 //   3. removal requests are sorted by row; build_unlink_kernel, one warp per distinct row,
 //      drops the owners that pruned it.
 //
+// Batch members do not see each other in phase 1 (they search the snapshot).  The links the sequential loop
+// would have made between them are recovered by a "mates" pass between phases 1 and 2 (build_mates_kernel):
+// two new nodes that selected the same neighbour on a layer are candidates for each other; every new node
+// re-runs the selection heuristic over its own list plus its EARLIER mates (the later node is the one that
+// would have found the earlier one, :806-819), and the link requests are then regenerated from the final
+// rows, so that the earlier mate receives the reverse link like any other selected neighbour (:820).
+//
 // Links stay symmetric after every batch (Graph.Test.invariant, :217-225).  With a batch of
 // one node and the sequential link kernel the phases collapse to the reference's order.
 #pragma once
@@ -29,6 +36,7 @@ namespace hb {
 constexpr int REQ_VBITS = 24;            // link request  = row id << 24 | index of the new node in its batch
 constexpr int REM_ABITS = 31;            // unlink request = row id << 31 | owner that dropped the row's node
 constexpr int LINK_MCAP = 96;            // incoming new nodes one row considers per batch
+constexpr int MATE_SPAN = 8;             // earlier batch members proposed to a new node per shared neighbour
 constexpr uint32_t ROW_UPPER = 0x80000000u;   // row id: node id (layer 0) or ROW_UPPER | upper row index
 
 struct BuildParams {
@@ -38,6 +46,7 @@ struct BuildParams {
   const int8_t* level;      // [n_total]
   const int32_t* row_owner; // [rowsU] node that owns each upper row
   int n0, B;                // this batch = nodes [n0, n0 + B)
+  const int32_t* order;     // phase 1 takes the batch in this order (multi-layer nodes, the long inserts, first); null = as numbered
   int sel0, selU;           // neighbours selected for a new node on layer 0 / above (:818)
   int cap0, capU;           // degree bound of a row before it is re-selected (:822-823)
   int keep_all;             // Hnsw.Ba shortcut: #candidates <= n keeps all (hnsw_algo.ml:596-599)
@@ -53,6 +62,7 @@ struct BuildParams {
   const unsigned int* head_count;
   unsigned int n_req;             // number of sorted requests (phase 2 / 3)
   unsigned int* next;             // work counter
+  int mate_mode;                  // link kernel: the rows are the new nodes' own, the incoming nodes their earlier mates
   unsigned long long* counters;   // [0] distance evaluations, [1] adjacency rows read, [2] dropped incoming, [3] rem overflow
 };
 
@@ -70,10 +80,12 @@ __device__ __forceinline__ uint32_t row_id(const GraphView& g, uint32_t node, in
 // `qe`/`qs2` receive the candidate's vector.  The kept list is scanned oldest first, eight
 // nodes per round, stopping at the first round that rejects (the reference's for_all scans
 // newest first and stops at the first failure: same verdict, different distance count).
-template <int CPL>
+// QREG = false: the candidate's vector is kept in shared memory only (qs2, zero padded to `q_chunks`), as the
+// search kernel keeps its query — fewer live registers, more resident warps.
+template <int CPL, bool QREG = true>
 __device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* cand, int ncand, int want, int keep_all,
                                                  uint32_t* sel, float4* qe, float4* qs2, float* newd, int lane,
-                                                 uint32_t& n_dist, Stage* st = nullptr) {
+                                                 uint32_t& n_dist, Stage* st = nullptr, int q_chunks = 0) {
   int nsel = 0;
   if (want <= 0) return 0;
   if (keep_all && ncand <= want) {
@@ -87,10 +99,11 @@ __device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* c
     const float de = key_dist(key);
     bool ok = true;
     if (nsel > 0) {
-      load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)e * g.ld4, qe, qs2, lane);
+      if (QREG || CPL == 0) load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)e * g.ld4, qe, qs2, lane);
+      else load_target_smem(g, reinterpret_cast<const float4*>(g.vec) + (size_t)e * g.ld4, qs2, q_chunks, lane);
       for (int base = 0; base < nsel; base += 8) {
         int cnt = min(8, nsel - base);
-        batch_dist<CPL>(g, qe, qs2, sel + base, newd, cnt, lane, st);
+        batch_dist<CPL>(g, QREG ? qe : nullptr, qs2, sel + base, newd, cnt, lane, st);
         n_dist += cnt;
         bool bad = lane < cnt && !(de < newd[lane]);
         unsigned any_bad = __ballot_sync(FULL, bad);
@@ -109,8 +122,8 @@ __device__ __forceinline__ int select_neighbours(const GraphView& g, uint64_t* c
 }
 
 // ---- phase 1 --------------------------------------------------------------------------------------
-template <int CPL, bool GANG = false>
-__global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp) {
+template <int CPL, bool GANG = false, bool QREG = true>
+__global__ void __launch_bounds__(256, QREG ? 2 : 3) build_search_kernel(const BuildParams bp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SearchParams& p = bp.sp;
   const GraphView& g = p.g;
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   // batches smaller than the resident warps run a gang of p.gang warps per insert (search.cuh, Gang): the
   // distance rounds of every expansion are shared, the insert's latency — which is the batch's — drops
   unsigned char* my = smem_raw + (size_t)(GANG ? warp / p.gang : warp) * bp.smem_per_warp;
-  WarpCtx<CPL> w;
+  WarpCtx<CPL, QREG> w;
   w.lane = lane;
   w.gang.P = GANG ? p.gang : 1; w.gang.rank = GANG ? warp % p.gang : 0; w.gang.bar = GANG ? 1 + warp / p.gang : 1;
   w.gang.job = reinterpret_cast<GangJob*>(my + bp.smem_per_warp - (int)sizeof(GangJob));
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
   uint32_t* sel = reinterpret_cast<uint32_t*>(qs2 + p.q_smem_chunks);
   stage_attach(w.st, reinterpret_cast<unsigned char*>(sel + bp.sel_cap), p.stage_slots, p.stage_ahead, g.ld4, lane);
   w.tie_spill = nullptr; w.tie_slot = -1;
-  float4 qe[CPL > 0 ? CPL : 1];
+  float4 qe[(CPL > 0 && QREG) ? CPL : 1];
 
   unsigned long long tot_dist = 0, tot_exp = 0;
   while (true) {
@@ -141,9 +154,10 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
     if (lane == 0) b = atomicAdd(bp.next, 1u);
     b = __shfl_sync(FULL, b, 0);
     if (b >= (unsigned)bp.B) break;
+    if (bp.order) b = (unsigned)bp.order[b];
     const uint32_t v = (uint32_t)bp.n0 + b;
-    load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)v * g.ld4, w.q, w.qs, lane);
-    if (GANG && CPL > 0)                            // the gang reads the target from shared memory
+    if (QREG || CPL == 0) load_target<CPL>(g, reinterpret_cast<const float4*>(g.vec) + (size_t)v * g.ld4, w.q, w.qs, lane);
+    if ((GANG || !QREG) && CPL > 0)                 // the gang (and the register-lean build) reads the target from shared memory
       load_target_smem(g, reinterpret_cast<const float4*>(g.vec) + (size_t)v * g.ld4, w.qs, p.q_smem_chunks, lane);
     const int lv = bp.level[v];
     uint32_t n_dist = 0, n_exp0 = 0, n_expU = 0;
@@ -175,12 +189,12 @@ __global__ void __launch_bounds__(256) build_search_kernel(const BuildParams bp)
       }
       w.vis.count = n;
       __syncwarp();
-      layer_search<CPL, true, GANG>(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
+      layer_search<CPL, QREG, GANG>(p, w, layer, n, n_dist, layer == 0 ? n_exp0 : n_expU, tie_overflow);
       visited_release(w.vis, p, lane);
       __syncwarp();
       // select_neighbours (MinQueue.copy w_queue) nc (:818-819)
       const int want = layer == 0 ? bp.sel0 : bp.selU;
-      int nsel = select_neighbours<CPL>(g, w.keys, n, want, bp.keep_all, sel, qe, qs2, w.newd, lane, n_dist, &w.st);
+      int nsel = select_neighbours<CPL, QREG>(g, w.keys, n, want, bp.keep_all, sel, qe, qs2, w.newd, lane, n_dist, &w.st, p.q_smem_chunks);
       // set_connections_for_new_node (:820): Neighbours.add prepends, so the row head is the
       // last node selected; the reverse half is deferred to the link phase
       int32_t* row = row_ptr(bp, row_id(g, v, layer));
@@ -216,6 +230,68 @@ __global__ void segment_heads_kernel(const uint64_t* keys, unsigned n, int shift
   if (lane == __ffs(m) - 1) base = atomicAdd(head_count, (unsigned)__popc(m));
   base = __shfl_sync(FULL, base, __ffs(m) - 1);
   if (head) heads[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+// ---- batch mates -------------------------------------------------------------------------------------
+// `sorted` = phase 1's requests ordered by (row, batch index).  Request i = (row of w, v_i): every one of
+// the up to MATE_SPAN requests before it in the same segment names an earlier batch member v_j that
+// selected the same w on the same layer; emit (row of v_i on that layer, v_j).  Duplicates (two shared
+// neighbours) are dropped by the link kernel after the sort.
+__global__ void build_mates_kernel(const BuildParams bp, const uint64_t* sorted, unsigned n_req, uint64_t* mates,
+                                   unsigned int* mate_count) {
+  const GraphView& g = bp.sp.g;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint64_t vmask = (1ull << REQ_VBITS) - 1;
+  uint64_t out[MATE_SPAN];
+  int k = 0;
+  if (i < n_req) {
+    const uint64_t key = sorted[i];
+    const uint32_t rid = (uint32_t)(key >> REQ_VBITS);
+    int layer = 0;
+    if (rid & ROW_UPPER) { const uint32_t r = rid & ~ROW_UPPER; layer = (int)r - g.upper_off[bp.row_owner[r]] + 1; }
+    uint64_t mine = 0;
+    for (unsigned t = 1; t <= (unsigned)MATE_SPAN && t <= i; t++) {
+      const uint64_t kj = sorted[i - t];
+      if ((uint32_t)(kj >> REQ_VBITS) != rid) break;
+      if (k == 0) mine = (uint64_t)row_id(g, (uint32_t)bp.n0 + (uint32_t)(key & vmask), layer) << REQ_VBITS;
+      out[k++] = mine | (kj & vmask);
+    }
+  }
+  int incl = k;
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+  const int total = __shfl_sync(FULL, incl, 31);
+  if (!total) return;
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(mate_count, (unsigned)total);
+  base = __shfl_sync(FULL, base, 31) + (unsigned)(incl - k);
+#pragma unroll
+  for (int t = 0; t < MATE_SPAN; t++) if (t < k) mates[base + t] = out[t];
+}
+
+// Link requests from the final rows of the batch's new nodes (one warp per node): (row of x on the layer, v)
+// for every x in v's list.
+__global__ void __launch_bounds__(256) build_requests_kernel(const BuildParams bp) {
+  const GraphView& g = bp.sp.g;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < bp.B; b += warps) {
+    const uint32_t v = (uint32_t)bp.n0 + (uint32_t)b;
+    for (int layer = min((int)bp.level[v], g.max_layer); layer >= 0; layer--) {
+      const int32_t* row = row_ptr(bp, row_id(g, v, layer));
+      const int slots = layer == 0 ? g.slots0 : g.slotsU;
+      for (int r0 = 0; r0 < slots; r0 += 32) {
+        const int nb = r0 + lane < slots ? row[r0 + lane] : -1;
+        const unsigned m = __ballot_sync(FULL, nb >= 0);
+        if (!m) break;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(bp.req_count, (unsigned)__popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (nb >= 0) bp.req[base + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)row_id(g, (uint32_t)nb, layer) << REQ_VBITS) | (uint64_t)b;
+        if (m != FULL) break;
+      }
+    }
+  }
 }
 
 // Rank sort of n distinct keys (shared memory, one warp).
@@ -266,17 +342,26 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
     const uint32_t rid = (uint32_t)(k0 >> REQ_VBITS);
     // incoming new nodes of this row, ascending id (the order the sequential loop adds them)
     int m = 0;
+    uint32_t* inc = reinterpret_cast<uint32_t*>(sorted);       // mate mode: the distinct incoming ids, ascending
     for (unsigned i = h;; i += 32) {
       unsigned idx = i + lane;
-      bool in = idx < bp.n_req && (uint32_t)(bp.req[idx] >> REQ_VBITS) == rid;
+      const uint64_t key = idx < bp.n_req ? bp.req[idx] : 0ull;
+      bool in = idx < bp.n_req && (uint32_t)(key >> REQ_VBITS) == rid;
       unsigned bm = __ballot_sync(FULL, in);
-      m += __popc(bm);
+      if (bp.mate_mode) {                                      // the same mate can be proposed through several shared neighbours
+        const bool fresh = in && (idx == h || bp.req[idx - 1] != key);
+        const unsigned fm = __ballot_sync(FULL, fresh);
+        const int pos = m + __popc(fm & ((1u << lane) - 1u));
+        if (fresh && pos < LINK_MCAP) inc[pos] = (uint32_t)bp.n0 + (uint32_t)(key & ((1ull << REQ_VBITS) - 1));
+        m += __popc(fm);
+      } else m += __popc(bm);
       if (bm != FULL) break;
     }
+    __syncwarp();
     int32_t* row = row_ptr(bp, rid);
     const bool upper = (rid & ROW_UPPER) != 0;
     const int slots = upper ? g.slotsU : g.slots0;
-    const int nc = upper ? bp.capU : bp.cap0;
+    const int nc = bp.mate_mode ? (upper ? bp.selU : bp.sel0) : (upper ? bp.capU : bp.cap0);
     uint32_t a;                                       // the row's owner
     int layer;
     if (upper) { uint32_t r = rid & ~ROW_UPPER; a = (uint32_t)bp.row_owner[r]; layer = (int)r - g.upper_off[a] + 1; }
@@ -285,20 +370,30 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
     // union, list order: newest incoming first, then the old row (:116-118 prepend)
     int dropped_inc = 0;
     int mm = m;
-    if (mm > LINK_MCAP) { dropped_inc = mm - LINK_MCAP; mm = LINK_MCAP; }   // keeps the LINK_MCAP smallest ids
+    if (mm > LINK_MCAP) { dropped_inc = bp.mate_mode ? 0 : mm - LINK_MCAP; mm = LINK_MCAP; }   // keeps the LINK_MCAP smallest ids
     for (int j = lane; j < mm; j += 32)
-      uid[mm - 1 - j] = (uint32_t)bp.n0 + (uint32_t)(bp.req[h + j] & ((1ull << REQ_VBITS) - 1));
+      uid[mm - 1 - j] = bp.mate_mode ? inc[j] : (uint32_t)bp.n0 + (uint32_t)(bp.req[h + j] & ((1ull << REQ_VBITS) - 1));
     int deg = 0;
     for (int r0 = 0; r0 < slots; r0 += 32) {
       int nb = r0 + lane < slots ? row[r0 + lane] : -1;
       unsigned bm = __ballot_sync(FULL, nb >= 0);
-      if (nb >= 0) uid[mm + r0 + lane] = (uint32_t)nb;
-      deg += __popc(bm);
+      if (bp.mate_mode) {
+        // a later round: the row may already hold a proposed mate (a member of this batch) — it stays in its place once
+        bool keep = nb >= 0;
+        if (keep && nb >= bp.n0)
+          for (int j = 0; j < mm; j++) if (inc[j] == (uint32_t)nb) { keep = false; break; }
+        const unsigned km = __ballot_sync(FULL, keep);
+        if (keep) uid[mm + deg + __popc(km & ((1u << lane) - 1u))] = (uint32_t)nb;
+        deg += __popc(km);
+      } else {
+        if (nb >= 0) uid[mm + r0 + lane] = (uint32_t)nb;
+        deg += __popc(bm);
+      }
       if (bm != FULL) break;
     }
     __syncwarp();
     const int u = mm + deg;
-    if (u <= nc && dropped_inc == 0) {
+    if (!bp.mate_mode && u <= nc && dropped_inc == 0) {
       for (int j = lane; j < u; j += 32) row[j] = (int32_t)uid[j];
       __syncwarp();
       continue;
@@ -310,9 +405,14 @@ __global__ void __launch_bounds__(256) build_link_kernel(const BuildParams bp) {
     for (int j = lane; j < u; j += 32) ukey[j] = make_key(ud[j], uid[j]);
     __syncwarp();
     warp_rank_sort(ukey, sorted, u, lane);
-    int nsel = select_neighbours<CPL>(g, sorted, u, nc, 0, sel, qe, qs2, newd, lane, n_dist, &st);   // :824-826
+    int nsel = select_neighbours<CPL>(g, sorted, u, nc, bp.mate_mode ? bp.keep_all : 0, sel, qe, qs2, newd, lane, n_dist, &st);   // :824-826
     // Graph.set_connections (:182-196): the row becomes the selected list (head = last kept) ...
     for (int j = lane; j < slots; j += 32) row[j] = j < nsel ? (int32_t)sel[nsel - 1 - j] : -1;
+    if (bp.mate_mode) {            // nothing is linked to this row yet: the requests are regenerated from the rows
+      tot_dist += n_dist;
+      __syncwarp();
+      continue;
+    }
     // ... and every member that fell out loses its link to the owner
     const int nrem = u - nsel + dropped_inc;
     unsigned base = 0;

@@ -100,6 +100,9 @@ struct hnswb200_index {
   int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
   int64_t param_stage_ahead = -1;       // rows beyond the ring prefetched to L2 (-1 auto, 0..31)
   int64_t param_gang = 0;               // warps per query: 0 auto (1 when the batch fills the GPU), 1, 2, 4
+  int64_t param_build_ratio_early = 4;  // build: a batch is at most 1/this of the graph so far (and 1/build_ratio of the final graph)
+  int64_t param_build_mates = 1;        // build: 1 = members of a batch are proposed to each other (build.cuh, mates), 0 = they never link
+  int64_t param_build_qreg = 0;         // build: 1 = the new node's vector in registers (fewer resident warps), 0 = in shared memory
   int64_t param_hash_bits = 0;          // visited hash entries: 0 auto (16-bit quotiented when the id range allows), 16, 32
   unsigned int* h_ready = nullptr;      // pinned: the "pieces ready" values the copy stream writes after each piece
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -115,8 +118,10 @@ struct hnswb200_index {
   bool search_pending = false;          // ev1 marks the end of the last enqueued search (calls on one index are serialised on the device)
   bool poisoned = false;                // a build batch failed half-way: the graph may hold links to nodes that do not exist
   // build scratch
-  DevBuf<uint64_t> b_req, b_req_sorted, b_rem, b_rem_sorted;
+  DevBuf<uint64_t> b_req, b_req_sorted, b_rem, b_rem_sorted, b_mate, b_mate_sorted;
   DevBuf<unsigned int> b_heads, b_ctr;
+  DevBuf<int32_t> b_order;
+  std::vector<int32_t> h_order;
   DevBuf<unsigned long long> b_counters;
   DevBuf<unsigned char> b_cub;
   int64_t param_build_ratio = 64, param_max_warps_per_sm = 0, param_visited_mode = 0;   // 0 auto, 1 hash, 2 bitset
@@ -732,6 +737,9 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "stage_rows") x->param_stage_rows = value;
     else if (s == "stage_ahead") x->param_stage_ahead = value;
     else if (s == "hash_bits") x->param_hash_bits = value;
+    else if (s == "build_qreg") x->param_build_qreg = value;
+    else if (s == "build_mates") x->param_build_mates = value;
+    else if (s == "build_ratio_early") x->param_build_ratio_early = value;
     else if (s == "gang") {
       if (value != 0 && value != 1 && value != 2 && value != 4) fail(HNSWB200_EINVAL, "gang must be 0 (automatic), 1, 2 or 4");
       x->param_gang = value;

@@ -381,3 +381,66 @@ def test_gang_build_is_the_one_warp_build():
         gs.append(h.export_graph())
     for g in gs[1:]:
         _same_graph(g, gs[0])
+
+
+def _build_with(X, lv, M, efC, **params):
+    h = Ohnsw.Hgraph(X.shape[1], Ohnsw.distance_l2, M, efC)
+    for k, v in params.items():
+        h.set_param(k, v)
+    capi.check(capi.lib().hnswb200_build(h._h, capi.ptr(X), len(X), capi.ptr(lv)))
+    return h
+
+
+def test_build_kernel_variants_and_order_do_not_change_the_graph():
+    """Phase 1 has two instances (the new node's vector in registers / in shared memory only) and takes a large
+    batch longest-insert-first; every insert sees the same snapshot whichever warp runs it and whenever, so the
+    graph must not depend on either."""
+    X = H.sift_like(40000, 128, seed=78)
+    lv = draw_levels(len(X), 16)
+    gs = [_build_with(X, lv, 16, 100, build_qreg=q).export_graph() for q in (0, 1, 2)]
+    for g in gs[1:]:
+        _same_graph(g, gs[0])
+
+
+def test_mates_pass_links_batch_members_and_keeps_the_invariants():
+    """10 000 nodes enter a 20 000-node graph as ONE batch.  Without the mates pass members of a batch never link
+    to each other and recall drops; with it (build.cuh) the links the sequential loop would have made between
+    them are back.  The structural invariants hold either way."""
+    n0, n, M, efC = 20000, 30000, 16, 100
+    X = H.sift_like(n, 128, seed=79)
+    Q = H.sift_like(2000, 128, seed=80)
+    lv = draw_levels(n, M)
+    lv[n0:] = np.minimum(lv[n0:], lv[:n0].max())          # a node that raises the top layer would close the batch
+    gt, _ = H.brute_force_knn_l2(X, Q, 10, return_ids=True)
+    rec, links = {}, {}
+    for mates in (0, 1):
+        h = _build_with(X[:n0], lv[:n0], M, efC)
+        h.set_param("build_ratio", 1); h.set_param("build_ratio_early", 1); h.set_param("build_mates", mates)
+        launches = h.stats().gpu_launches
+        capi.check(capi.lib().hnswb200_insert(h._h, capi.ptr(X[n0:]), n - n0, capi.ptr(lv[n0:])))
+        assert h.stats().gpu_launches - launches < 40      # one batch
+        g = h.export_graph()
+        _check_structure(g, lv, M)
+        rec[mates] = H.Recall.ids(gt, Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=32)[0])
+        src = np.repeat(np.arange(n), g.degree(0))
+        links[mates] = int(((src >= n0) & (g.nbrs[0] >= n0)).sum())
+    assert links[0] == 0 and links[1] > 0, links
+    assert rec[1] > rec[0] + 0.003, rec
+
+
+def test_default_schedule_uses_few_batches_and_matches_fine_batches():
+    """Default schedule: a batch is at most 1/64 of the final graph and 1/4 of the graph so far (early rows are
+    re-selected many times as the graph grows, so coarse early batches leave no trace).  Against batches of
+    1/64 of the graph so far throughout — round 1's schedule — recall is the same and the launch count far lower."""
+    n, M, efC = 50000, 16, 100
+    X = H.sift_like(n, 128, seed=81)
+    Q = H.sift_like(2000, 128, seed=82)
+    lv = draw_levels(n, M)
+    gt, _ = H.brute_force_knn_l2(X, Q, 10, return_ids=True)
+    h_def = _build_with(X, lv, M, efC)
+    h_fine = _build_with(X, lv, M, efC, build_ratio_early=64)
+    assert h_def.stats().gpu_launches < h_fine.stats().gpu_launches / 2
+    for ef in (16, 64):
+        r_def = H.Recall.ids(gt, Ohnsw.knn_batch_bigarray(h_def, Q, k=10, ef=ef)[0])
+        r_fine = H.Recall.ids(gt, Ohnsw.knn_batch_bigarray(h_fine, Q, k=10, ef=ef)[0])
+        assert abs(r_def - r_fine) <= 0.005, (ef, r_def, r_fine)
