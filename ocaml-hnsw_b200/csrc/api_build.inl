@@ -158,9 +158,35 @@ struct BuildTrace {
 };
 BuildTrace g_trace;
 
+// The new vectors travel to the device in pieces on a copy stream while the first batches are built: a batch
+// only needs the rows below its own end.  (The source is the caller's pageable memory: one 512 MB copy in
+// front of the build costs ~50 ms in which the GPU does nothing.)
+struct RowUploader {
+  hnswb200_index* x = nullptr;
+  const float* src = nullptr;     // [n_new][dim]
+  int64_t base = 0, total = 0;    // device rows [base, base + total)
+  int64_t sent = 0;               // rows handed to the copy stream so far
+  bool unseen = false;            // pieces sent since the build stream last waited for the copy stream
+  static constexpr int64_t PIECE_BYTES = 48ll << 20;
+  int64_t piece_rows() const { return std::max<int64_t>(1024, PIECE_BYTES / ((int64_t)x->ld * 4)); }
+  void send(int64_t upto) {       // make sure rows below `upto` (relative to base) are on their way
+    upto = std::min(upto, total);
+    if (upto <= sent) return;
+    upload_rows(x->vec.p + (size_t)(base + sent) * x->ld, x->ld, src + (size_t)sent * x->dim, x->dim, upto - sent, x->copy_stream);
+    CUDA_CHECK(cudaEventRecord(x->copy_event, x->copy_stream));
+    sent = upto; unseen = true;
+  }
+  void need(int64_t upto, cudaStream_t s) {   // the work enqueued on `s` from here on reads rows below `upto`
+    if (upto > sent) send(std::max(upto, std::min(total, sent + piece_rows())));
+    if (unseen) { CUDA_CHECK(cudaStreamWaitEvent(s, x->copy_event, 0)); unseen = false; }
+  }
+  void idle_piece() { if (sent < total) send(sent + piece_rows()); }   // called while a long kernel runs
+};
+
 // One batch: nodes [n0, n0 + B) against the graph of nodes [0, n0).
-void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, int64_t n_total) {
+void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, int64_t n_total, RowUploader* up = nullptr) {
   cudaStream_t s = x->stream;
+  if (up) up->need(n0 + B - up->base, s);
   const SearchPlan& pl = bpl.sp;
   // request capacity: one per selected neighbour per layer
   size_t req_cap = 0;
@@ -228,6 +254,7 @@ void run_batch(hnswb200_index* x, const BuildPlan& bpl, int64_t n0, int64_t B, i
     default: launch_build_search<0>(p, pl, grid, true, s); break;
   }
   x->st.gpu_launches += 1;
+  if (up && B >= 2048) up->idle_piece();            // the host would only wait for phase 1 now: stage the next piece instead
   unsigned ctr[CTR_N];
   CUDA_CHECK(cudaMemcpyAsync(ctr, x->b_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -419,7 +446,16 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   CUDA_CHECK(cudaMemsetAsync(x->adj0.p + (size_t)n_old * x->slots0, 0xff, (size_t)n_new * x->slots0 * 4, s));
   if (rows > rows_old)
     CUDA_CHECK(cudaMemsetAsync(x->adjU.p + (size_t)rows_old * x->slotsU, 0xff, (size_t)(rows - rows_old) * x->slotsU * 4, s));
-  upload_rows(x->vec.p + (size_t)n_old * x->ld, x->ld, data, x->dim, n_new, s);
+  RowUploader up;
+  up.x = x; up.src = data; up.base = n_old; up.total = n_new;
+  if (!x->copy_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&x->copy_event, cudaEventDisableTiming));
+  }
+  // the copy stream must not write into storage that `s` is still moving (reserve(keep) copies on s)
+  CUDA_CHECK(cudaEventRecord(x->copy_event, s));
+  CUDA_CHECK(cudaStreamWaitEvent(x->copy_stream, x->copy_event, 0));
+  up.send(up.piece_rows());
   CUDA_CHECK(cudaMemcpyAsync(x->upper_off.p + n_old, uoff_new.data(), (size_t)n_new * 4, cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(x->level.p + n_old, lvl_new.data(), (size_t)n_new, cudaMemcpyHostToDevice, s));
   if (!owner_new.empty())
@@ -487,14 +523,15 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
     // every later insert: it closes its batch
     for (int64_t j = 0; j < B; j++)
       if (x->h_level[(size_t)(done + j)] > x->max_layer) { B = j + 1; break; }
-    run_batch(x, bpl, done, B, n_tot);
+    run_batch(x, bpl, done, B, n_tot, &up);
     const int64_t last = done + B - 1;
     if (x->h_level[(size_t)last] > x->max_layer) { x->max_layer = x->h_level[(size_t)last]; x->entry = last; }
     done += B;
     x->n = done;
   }
+  up.need(n_new, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
-  } catch (...) { rollback(); throw; }
+  } catch (...) { cudaStreamSynchronize(x->copy_stream); rollback(); throw; }
   unsigned long long c[4];
   CUDA_CHECK(cudaMemcpy(c, x->b_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
   unsigned long long evs[2];

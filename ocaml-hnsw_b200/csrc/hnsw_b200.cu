@@ -95,6 +95,8 @@ struct hnswb200_index {
   // scratch
   cudaStream_t stream = nullptr;
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // host-buffer search: copy / compute overlap
+  cudaStream_t copy_stream = nullptr;   // build: the new vectors are uploaded in pieces while the first batches run
+  cudaEvent_t copy_event = nullptr;
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t param_host_chunks = 0;
   int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
@@ -761,6 +763,8 @@ int hnswb200_destroy(hnswb200_index* x) {
     if (x->ev0) cudaEventDestroy(x->ev0);
     if (x->ev1) cudaEventDestroy(x->ev1);
     if (x->h_ready) cudaFreeHost(x->h_ready);
+    if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
+    if (x->copy_event) cudaEventDestroy(x->copy_event);
     for (cudaStream_t a : x->aux_stream) if (a) cudaStreamDestroy(a);
     for (cudaEvent_t e : x->aux_event) if (e) cudaEventDestroy(e);
     if (x->stream) cudaStreamDestroy(x->stream);
