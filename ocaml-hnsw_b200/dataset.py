@@ -32,6 +32,24 @@ class Dataset:
         return Dataset(train, test, d, test_ids=ids)
 
     @staticmethod
+    def read_hdf5(path, limit_train=None, limit_test=None):
+        """Dataset.read (benchmark/dataset.ml:76-102) on an ann-benchmarks HDF5 file: the `train`, `test` and
+        `distances` float32 datasets and the `distance` attribute of the root group, cropped like the reference's
+        ?limit_train / ?limit_test (sub_right on the Fortran-layout matrix = the first rows here).  No libhdf5
+        in this image: the file is parsed by hdf5min.py."""
+        from .hdf5min import Hdf5File
+        with Hdf5File(path) as f:
+            distance = f.attrs.get("distance")
+            if not isinstance(distance, str):
+                raise ValueError(f"{path}: no `distance` string attribute")
+            # Distance.of_string (dataset.ml:10-12): "euclidean" -> Euclidean, anything else -> Unknown x (kept as is)
+            train = np.ascontiguousarray(f.read("train", limit_train), np.float32)
+            test = np.ascontiguousarray(f.read("test", limit_test), np.float32)
+            dists = np.ascontiguousarray(f.read("distances", limit_test), np.float32)
+            ids = np.ascontiguousarray(f.read("neighbors", limit_test), np.int32) if "neighbors" in f else None
+        return Dataset(train, test, dists, distance, test_ids=ids)
+
+    @staticmethod
     def random(dim, num_train, num_test, k, seed=(1234, 4321), device=0):
         """Dataset.random (benchmark/dataset.ml:47-58): Lacaml.S.Mat.random = uniform [-1, 1)."""
         train = (np.random.default_rng(seed[0]).random((num_train, dim), dtype=np.float32) * 2 - 1)
