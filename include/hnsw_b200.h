@@ -129,8 +129,14 @@ int hnswb200_create(hnswb200_index** out, int dim, int metric, int M, int ef_con
 int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
 /* Tunables (0 = automatic): "hash_slots" (visited hash slots per query), "visited_mode" (1 = shared
  * memory hash, 2 = global bitset), "warps_per_cta", "max_warps_per_sm", "build_batch" (max inserts
- * per GPU batch, default 16384; 1 = sequential inserts), "build_ratio" (a batch is at most
- * n / build_ratio nodes, default 64), "host_chunks" (2..8: hnswb200_search streams batches of
+ * per GPU batch, default 16384; 1 = sequential inserts: the reference's own order, edge for edge),
+ * "build_ratio" (a batch is at most 1 / build_ratio of the graph the call will end with, default 64),
+ * "build_ratio_early" (... and at most 1 / this of the graph so far, default 4: early rows are re-selected
+ * many times as the graph grows, so coarse early batches leave no trace in the finished index),
+ * "build_mates" (default 1: members of a batch that selected the same neighbour are proposed to each other,
+ * which restores the links the sequential loop would have made between them; 0 = batch members never link),
+ * "build_qreg" (phase 1 of the build: 0 = automatic, 1 = new node's vector in registers, 2 = in shared memory
+ * only; same graph either way), "host_chunks" (2..8: hnswb200_search streams batches of
  * >= 4096 queries to the GPU in this many pieces behind ONE already running search kernel whose
  * warps wait for the piece that holds their query; default: copy first, then search),
  * "stage_rows" (rows of >= 1 KB are gathered with cp.async.bulk into a per-warp shared-memory ring of
@@ -140,7 +146,9 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
  * 32 = plain ids), "gang" (warps working on one query / one insert when a batch is smaller than the GPU:
  * 0 = automatic, 1 = never, 2 or 4),
  * "row_floats" (stride of a vector row in floats, a multiple of 4 >= dim; default dim rounded up to
- * 4; only on an empty index).  None of them changes a result: only where data sits and who computes it. */
+ * 4; only on an empty index).  Apart from the three batch-schedule parameters of the build (build_batch, build_ratio*,
+ * build_mates — a batched build is checked by recall, not edge by edge) none of them changes a result: only where
+ * data sits and who computes it. */
 int hnswb200_set_param(hnswb200_index* idx, const char* name, int64_t value);
 int hnswb200_destroy(hnswb200_index* idx);
 
