@@ -322,8 +322,15 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
     for (int s0 = 0; s0 < slots && row; s0 += p.nb_cap) {
       int total = 0;
       bool row_ended = false;
-      for (int r0 = s0; r0 < min(slots, s0 + p.nb_cap); r0 += 32) {
-        int nb = (r0 + lane < slots) ? __ldg(row + r0 + lane) : -1;
+      // both 32-slot chunks of a pass are sent for at once (rows wider than 32 slots: M > 16)
+      int nbs[2];
+      nbs[0] = (s0 + lane < slots) ? __ldg(row + s0 + lane) : -1;
+      nbs[1] = (p.nb_cap > 32 && s0 + 32 + lane < slots) ? __ldg(row + s0 + 32 + lane) : -1;
+#pragma unroll
+      for (int ci = 0; ci < 2; ci++) {
+        const int r0 = s0 + 32 * ci;
+        if (r0 >= min(slots, s0 + p.nb_cap)) break;
+        const int nb = nbs[ci];
         unsigned valid = __ballot_sync(FULL, nb >= 0);
         if (!valid) { row_ended = true; break; }
         if (!w.vis.bits && w.vis.count + 32u > w.vis.limit) visited_spill(w.vis, p, lane);
