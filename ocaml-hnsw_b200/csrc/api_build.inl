@@ -469,6 +469,7 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   const double t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // scratch
   BuildPlan bpl = plan_build(x, n_tot);
+  const double t_plan_only = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - t_setup;
   x->b_ctr.reserve(CTR_N);
   x->b_counters.reserve(4);
   x->d_events.reserve(4);
@@ -538,7 +539,8 @@ void append_nodes(hnswb200_index* x, const float* data, int64_t n_new, const int
   CUDA_CHECK(cudaMemcpy(evs, x->d_events.p, sizeof(evs), cudaMemcpyDeviceToHost));
   if (c[3]) fail(HNSWB200_ECUDA, "build: removal buffer overflow");
   if (g_trace.on) {
-    fprintf(stderr, "[hnsw_b200 build] storage + upload %.3fs, plan + scratch %.3fs\n", t_setup, t_plan);
+    fprintf(stderr, "[hnsw_b200 build] storage + upload %.3fs, plan (occupancy queries: first use loads the kernels) %.3fs, scratch + visited pool %.3fs\n",
+            t_setup, t_plan_only, t_plan - t_plan_only);
     fprintf(stderr, "[hnsw_b200 build] n=%lld batches=%lld (under one wave: %lld) search %.3fs mates %.3fs (%llu proposals) sort+heads %.3fs alloc %.3fs link %.3fs unlink-enqueue %.3fs dropped_incoming=%llu grid=%d x %d warps hash_slots=%d\n",
             (long long)n_new, (long long)g_trace.batches, (long long)g_trace.small, g_trace.t_search, g_trace.t_mates, (unsigned long long)g_trace.n_mates, g_trace.t_sort, g_trace.t_alloc, g_trace.t_link, g_trace.t_rest,
             c[2], bpl.sp.grid, bpl.sp.warps, bpl.sp.hash_slots);

@@ -197,9 +197,18 @@ __device__ __forceinline__ void visited_init(VisitedSet& v, const SearchParams& 
     v.limit = 0xffffffffu;
   }
 }
+// The set belongs to one warp and the ids of one call are distinct, so the test is a plain (L2) load and the
+// set a fire-and-forget reduction (RED, no return value to wait for): lanes that share a word each test their
+// own bit of the same old value.  __syncwarp orders a call's reductions before the next call's loads.
 __device__ __forceinline__ bool bitset_test_and_set(uint32_t* bits, uint32_t id) {
   const uint32_t bit = 1u << (id & 31);
+#ifdef HB_BITSET_ATOMIC
   return !(atomicOr(&bits[id >> 5], bit) & bit);
+#else
+  const bool is_new = !(__ldcg(&bits[id >> 5]) & bit);
+  if (is_new) atomicOr(&bits[id >> 5], bit);
+  return is_new;
+#endif
 }
 // Visited.mem / Visited.add for up to one id per lane (`active` lanes): true where the id was not yet
 // visited (and marks it).  All 32 lanes must call.  A lane whose id cannot be placed in the 16-bit
