@@ -414,33 +414,35 @@ __device__ __forceinline__ void layer_search(const SearchParams& p, WarpCtx<CPL,
           const unsigned am = __ballot_sync(FULL, acc);
           if (am) {
             const bool was_full = n == ef;
-            int rank = 0, minpos = 0x7fffffff;
+            int rank = 0;
             for (unsigned m = am; m; m &= m - 1u) {
               const int i = __ffs(m) - 1;
               const uint64_t ki = __shfl_sync(FULL, key, i);
-              const int pi = __shfl_sync(FULL, posK, i);
               rank += ki < key ? 1 : 0;
-              minpos = min(minpos, pi);
             }
+            const int minpos = __reduce_min_sync(FULL, acc ? posK : 0x7fffffff);
             const int f = posK + rank;                // my key's place in the merged order
-            // beam entries move up by the number of accepted keys below them; top chunk first
-            uint64_t ev_key = 0;
-            bool ev = false;
-            for (int base = (n - 1) & ~31; base >= (minpos & ~31); base -= 32) {
-              const int pos = base + lane;
-              const uint64_t kk = pos < n ? w.keys[pos] : 0ull;
-              int sh = 0;
-              for (unsigned m = am; m; m &= m - 1u) sh += __shfl_sync(FULL, posK, __ffs(m) - 1) <= pos ? 1 : 0;
+            // The merged beam, final position by final position, top chunk first: position p takes an accepted key
+            // (written by its owner below) or the old entry p - (accepted keys placed below p).  The accepted
+            // places of a chunk are one OR-reduction, the count below the chunk one ballot — no loop over the
+            // accepted keys per chunk.  Old entries that no longer fit (at most one per accepted key) are read first.
+            const int a_in = __popc(__ballot_sync(FULL, acc && f < ef));
+            const int nkeep = min(ef, n + __popc(am));
+            const int first_out = nkeep - a_in;       // old entries [first_out, n) fall off
+            const bool ev = first_out + lane < n;
+            const uint64_t ev_key = ev ? w.keys[first_out + lane] : 0ull;
+            for (int base = (nkeep - 1) & ~31; base >= (minpos & ~31); base -= 32) {
+              const unsigned word = __reduce_or_sync(FULL, (acc && (f & ~31) == base) ? 1u << (f & 31) : 0u);
+              const int below = __popc(__ballot_sync(FULL, acc && f < base));
+              const int pf = base + lane;
+              const bool old_here = pf < nkeep && !((word >> lane) & 1u);
+              const uint64_t kk = old_here ? w.keys[pf - below - __popc(word & ((1u << lane) - 1u))] : 0ull;
               __syncwarp();
-              if (pos < n && sh) {
-                if (pos + sh < ef) w.keys[pos + sh] = kk;
-                else { ev = true; ev_key = kk; }
-              }
+              if (old_here) w.keys[pf] = kk;
             }
             __syncwarp();
             if (acc && f < ef) w.keys[f] = key;
-            const int fmin = __reduce_min_sync(FULL, acc ? f : 0x7fffffff);
-            if (fmin < fu) fu = fmin;
+            if (minpos < fu) fu = minpos;           // the lowest accepted key has rank 0: its place is minpos
             n = min(ef, n + __popc(am));
             __syncwarp();
             if (n == ef) {
