@@ -67,6 +67,11 @@ extern "C" {
  * neighbour with distances to the INSERTED point (lib/hnsw_algo.ml:633-635,678-689), force-keeps candidates of
  * degree <= 1 (`do_not_isolate`, :591-592), descends upper layers with a heap (:393-437) and orders its lists
  * by pairing-heap / Base.Map fold order; none of that is pinned by a reference test and none is reproduced.
+ * Why the prune is not: the overflowing list contains the inserted point itself at distance 0, so it is kept
+ * first, and every other member e is then tested with `distance e point > e.distance_to_target` (:578-583) — the
+ * same two vectors on both sides, never true — so a pruned node keeps ONLY the inserted point plus its
+ * degree-<=1 members: each overflow wipes a node's list (the reason `do_not_isolate` was added, :584-587, and,
+ * one presumes, why benchmark.ml moved to path B).  A drop-in that reproduced it would reproduce the recall loss.
  * Search on an imported path-A graph (id_base = 1) follows path A's acceptance rule exactly. */
 #define HNSWB200_FLAVOUR_OHNSW 0
 #define HNSWB200_FLAVOUR_HNSW_BA 1
