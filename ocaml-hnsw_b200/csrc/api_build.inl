@@ -65,10 +65,10 @@ BuildPlan plan_build(hnswb200_index* x, int64_t n_total) {
   // phase 1: the search plan for ef = efC plus the second target copy and the selected list
   SearchPlan& pl = bp.sp;
   int ef = x->efC;
-  int chunks = x->ld / 4;
-  int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
+  const int chunks = x->ld / 4, used = x->real_chunks();
+  int cpl = (used + hb::TEAM - 1) / hb::TEAM;
   pl.cpl = cpl <= 4 ? cpl : 0;
-  pl.q_chunks = pl.cpl ? hb::TEAM * pl.cpl : round_up(chunks, 2);      // (a gang reads the target from shared memory)
+  pl.q_chunks = pl.cpl ? hb::TEAM * pl.cpl : round_up(used, 2);      // (a gang reads the target from shared memory)
   pl.gang = 1;
   pl.ef_cap = round_up(ef, 32);
   pl.stage_slots = stage_slots_for(x, pl.cpl);

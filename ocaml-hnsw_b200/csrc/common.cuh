@@ -376,31 +376,50 @@ struct VisitedSet {
   uint32_t* bits;       // non-null once spilled
   int pool_slot;
 };
-// 1 = newly added, 0 = was present, 2 = could not be placed (16-bit format: displacement out of reach)
+// 32-bit entries: 1 = newly added, 0 = was present
 __device__ __forceinline__ int hash_test_and_set(uint32_t* tab, const HashCfg& hc, uint32_t id) {
-  if (!hc.bits16) {
-    const uint32_t key = id + 1u;
-    uint32_t h = __umulhi(id * 2654435761u, hc.slots);          // multiply-shift range reduction
-    while (true) {
-      const uint32_t old = atomicCAS(&tab[h], 0u, key);
-      if (old == 0u) return 1;
-      if (old == key) return 0;
-      h = h + 1u == hc.slots ? 0u : h + 1u;
-    }
+  const uint32_t key = id + 1u;
+  uint32_t h = __umulhi(id * 2654435761u, hc.slots);          // multiply-shift range reduction
+  while (true) {
+    const uint32_t old = atomicCAS(&tab[h], 0u, key);
+    if (old == 0u) return 1;
+    if (old == key) return 0;
+    h = h + 1u == hc.slots ? 0u : h + 1u;
   }
-  unsigned short* t16 = reinterpret_cast<unsigned short*>(tab);
+}
+// The 16-bit format for a whole warp at once (all 32 lanes call; the ids of the `active` lanes are distinct).
+// sm_100a has no 16-bit shared-memory CAS: `atomicCAS(unsigned short*)` is a spin loop around a 32-bit CAS,
+// ~18 instructions per probe (12 % of the search kernel's instructions on the GloVe shape, ncu).  The table
+// belongs to this warp alone, so the lanes only have to agree among themselves: every pending lane reads its
+// slot, an empty slot is claimed with a plain 16-bit store, and after a __syncwarp the lane whose value is still
+// there owns it (distinct ids give distinct entries for one slot, so the survivor is unambiguous); everybody
+// else moves one slot on.  Same table contents as the CAS version up to which of two racing ids takes the
+// nearer slot — membership, and so every result, is identical.
+// 1 = newly added, 0 = was present, 2 = could not be placed (displacement out of reach: the set spills).
+__device__ __forceinline__ int hash16_test_and_set_warp(uint32_t* tab, const HashCfg& hc, bool active, uint32_t id) {
+  volatile unsigned short* t16 = reinterpret_cast<volatile unsigned short*>(tab);
   const uint32_t x = (id * hc.mul) & hc.mask;
   const uint32_t q = __umulhi(x, hc.magic) >> hc.shift;
   uint32_t h = x - q * hc.slots;
-  const uint32_t dmax = 1u << hc.db;
-  for (uint32_t d = 0; d < dmax; d++) {
-    const unsigned short want = (unsigned short)(1u + ((q << hc.db) | d));
-    const unsigned short old = atomicCAS(&t16[h], (unsigned short)0, want);
-    if (old == 0) return 1;
-    if (old == want) return 0;
-    h = h + 1u == hc.slots ? 0u : h + 1u;
+  uint32_t want = 1u + (q << hc.db);                       // the entry for displacement 0; + d as the probe moves on
+  const uint32_t last = want + (1u << hc.db) - 1u;
+  int res = active ? -1 : 0;                               // -1: still looking
+  while (true) {
+    bool claimed = false;
+    if (res < 0) {
+      const uint32_t old = t16[h];
+      if (old == want) res = 0;
+      else if (old == 0u) { t16[h] = (unsigned short)want; claimed = true; }
+    }
+    __syncwarp();
+    if (res < 0) {
+      if (claimed && t16[h] == want) res = 1;
+      else if (want == last) res = 2;
+      else { want++; h = h + 1u == hc.slots ? 0u : h + 1u; }
+    }
+    if (!__any_sync(FULL, res < 0)) break;
   }
-  return 2;
+  return res;
 }
 // the id stored in slot `s` (0xffffffff if the slot is empty): used when the set moves to the bitset
 __device__ __forceinline__ uint32_t hash_decode(const uint32_t* tab, const HashCfg& hc, uint32_t s) {

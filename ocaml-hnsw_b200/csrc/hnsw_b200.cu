@@ -135,10 +135,14 @@ struct hnswb200_index {
   int last_k = 0, last_mode = 0;
   std::mutex mu;
 
+  // float4 chunks that hold components: a row stride wider than the vector (row_floats: 128-byte aligned rows for
+  // dim = 100) is padding the kernels never read
+  int real_chunks() const { return (dim + 3) / 4; }
+
   hb::GraphView view() const {
     hb::GraphView g;
     g.vec = vec.p; g.adj0 = adj0.p; g.upper_off = upper_off.p; g.adjU = adjU.p;
-    g.ld4 = ld / 4; g.chunks = ld / 4; g.slots0 = slots0; g.slotsU = slotsU;
+    g.ld4 = ld / 4; g.chunks = real_chunks(); g.slots0 = slots0; g.slotsU = slotsU;
     g.max_layer = max_layer; g.entry = (int)entry; g.n = (int)n; g.metric = metric;
     return g;
   }
@@ -302,10 +306,10 @@ int stage_ahead_for(const hnswb200_index* x) {
 
 SearchPlan plan_search(hnswb200_index* x, int ef, int64_t nq) {
   SearchPlan pl;
-  int chunks = x->ld / 4;
-  int cpl = (chunks + hb::TEAM - 1) / hb::TEAM;
+  const int chunks = x->ld / 4, used = x->real_chunks();      // row stride / chunks that hold components
+  int cpl = (used + hb::TEAM - 1) / hb::TEAM;
   pl.cpl = cpl <= 4 ? cpl : 0;                        // register-resident query up to 128 dims
-  pl.q_chunks = pl.cpl ? hb::TEAM * pl.cpl : round_up(chunks, 2);   // the target lives in shared memory
+  pl.q_chunks = pl.cpl ? hb::TEAM * pl.cpl : round_up(used, 2);   // the target lives in shared memory
   pl.ef_cap = round_up(ef, 32);
   // visited hash: ~42 slots per beam entry (a query evaluates ~25-30 distances per beam entry on
   // the 1M-row shapes), kept under 75 % load; anything larger continues on a global bitset

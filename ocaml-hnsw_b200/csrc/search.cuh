@@ -215,8 +215,9 @@ __device__ __forceinline__ bool bitset_test_and_set(uint32_t* bits, uint32_t id)
 // table makes the whole set move to the global bitset, where it is then placed.
 __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, const SearchParams& p, bool active, uint32_t id, int lane) {
   if (v.bits) return active && bitset_test_and_set(v.bits, id);
-  const int r = active ? hash_test_and_set(v.tab, p.hc, id) : 0;
-  if (!p.hc.bits16 || !__any_sync(FULL, r == 2)) return r == 1;
+  if (!p.hc.bits16) return active && hash_test_and_set(v.tab, p.hc, id) == 1;
+  const int r = hash16_test_and_set_warp(v.tab, p.hc, active, id);
+  if (!__any_sync(FULL, r == 2)) return r == 1;
   __syncwarp();
   visited_spill(v, p, lane);
   return r == 2 ? bitset_test_and_set(v.bits, id) : r == 1;

@@ -298,6 +298,35 @@ def test_device_queries_with_padded_rows():
         h.set_param("row_floats", 64)                      # not on a built index
 
 
+@pytest.mark.parametrize("dim,rf,metric", [(100, 128, capi.ANGULAR), (100, 128, capi.L2), (40, 128, capi.L2), (6, 32, capi.L2),
+                                           (300, 384, capi.L2)])
+def test_wider_row_stride_is_invisible(dim, rf, metric):
+    """row_floats: rows stored at a wider stride (128-byte aligned 400-byte rows for the GloVe shape, config C3).  The
+    padding is never read and never counted: ids, distances and work counters stay the oracle's, for a search on the
+    oracle's graph and for a sequential build (edge for edge)."""
+    X, Q = uniform(1000, dim, 61), uniform(64, dim, 62)
+    if metric != capi.L2:
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    M, efC = 12, 50
+    lv = draw_levels(len(X), M, 7)
+    lv[0] = 0
+    o = O.VecOracle(dim, metric).build(X, M, efC, lv)
+    h = Ohnsw.Hgraph(dim, metric, M, efC)
+    h.set_param("row_floats", rf)
+    h.import_graph(X, o.export())
+    _check(o, h, Q, 10, 10)
+    _check(o, h, Q, 10, 70)
+    hb = Ohnsw.Hgraph(dim, metric, M, efC)
+    hb.set_param("row_floats", rf)
+    hb.set_param("build_batch", 1)
+    capi.check(capi.lib().hnswb200_build(hb._h, capi.ptr(X), len(X), capi.ptr(lv)))
+    g, go = hb.export_graph(), o.export()
+    assert (g.n, g.max_layer, g.entry) == (go.n, go.max_layer, go.entry)
+    for l in range(go.max_layer + 1):
+        assert np.array_equal(g.offsets[l], go.offsets[l]) and np.array_equal(g.nbrs[l], go.nbrs[l])
+
+
 def test_hnsw_ba_acceptance_rule_on_tie_heavy_data():
     """HNSW_BA flavour: candidates that TIE with the beam's maximum are accepted (lib/hnsw.ml:494-506).
     Integer data makes ties the common case; ids, distances and counters must equal the oracle run
