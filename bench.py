@@ -617,7 +617,14 @@ def run_ours(a):
                                    "unit": "GB/s", "frac": bst.build_algorithmic_bytes / bst.build_seconds / 1e9 / peak,
                                    "algorithmic_bytes": bst.build_algorithmic_bytes}},
             "e2e": {"value": a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(Qp.nbytes),
-                    "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes), "recall_at_10": round(e2e_rec, 4),
+                    "d2h_bytes_per_step": int(out[0].nbytes + out[1].nbytes),
+                    # how those bytes cross PCIe every step: the buffers are pinned (hnswb200_host_register), so at N = 1 the
+                    # search kernel reads each query from host memory when a warp starts on it and stores each result row
+                    # into host memory when it is done (no cudaMemcpy, nothing kept on the device between steps); at N > 1 the
+                    # kernel reads its slice of the queries the same way and the merged rows come back with one D2H copy
+                    "transfer": ("in-kernel reads / writes of the pinned host buffers" if world == 1 else
+                                 "in-kernel reads of the pinned query slice, one D2H copy of the merged rows"),
+                    "recall_at_10": round(e2e_rec, 4),
                     "recall_compute_dataset_ml": round(e2e_rec_dist, 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -122,6 +122,8 @@ typedef struct hnswb200_stats {
   uint64_t search_tie_spills;        /* queries whose tie list continued in a global region (exact, just slower) */
   uint64_t build_dropped_incoming;   /* links dropped because one row received more than 96 new nodes in ONE build batch
                                         (the 96 smallest ids are kept and re-selected); 0 on every shape measured */
+  uint64_t search_zero_copy;         /* last hnswb200_search: bit 0 = the queries were read from the caller's pinned buffer by
+                                        the kernel itself, bit 1 = the result rows were stored straight into the caller's */
 } hnswb200_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -144,6 +146,8 @@ int hnswb200_set_flavour(hnswb200_index* idx, int flavour);
  * only; same graph either way), "host_chunks" (2..8: hnswb200_search streams batches of
  * >= 4096 queries to the GPU in this many pieces behind ONE already running search kernel whose
  * warps wait for the piece that holds their query; default: copy first, then search),
+ * "host_zero_copy" (default 1: hnswb200_search reads PINNED query buffers and writes PINNED result buffers from
+ * inside the kernel instead of copying them — see hnswb200_host_register; 0 = always copy),
  * "stage_rows" (rows of >= 1 KB are gathered with cp.async.bulk into a per-warp shared-memory ring of
  * this many rows, 4..32; 0 = automatic, -1 = per-lane 128-bit loads instead),
  * "stage_ahead" (rows beyond that ring sent for with a bulk L2 prefetch, 0..31; -1 = automatic),
@@ -182,7 +186,9 @@ int hnswb200_search(hnswb200_index* idx, const float* queries, int64_t nq, int k
 
 /* Same, all buffers already in this index's device memory: queries `float[nq][dim]` dense (any dim),
  * outputs `[nq][k]`.  `stream` is a cudaStream_t (NULL = the index's own stream; the call then
- * synchronises before returning, otherwise it only enqueues). */
+ * synchronises before returning, otherwise it only enqueues).  `d_queries` may also be a PINNED host buffer
+ * (hnswb200_host_register) here and in the _multi / _sharded variants: the kernel then reads every query from
+ * host memory when a warp starts on it, no copy. */
 int hnswb200_search_device(hnswb200_index* idx, const float* d_queries, int64_t nq, int k, int ef,
                            int mode, int32_t* d_ids, float* d_dists, void* stream);
 
@@ -293,7 +299,10 @@ int hnswb200_search_device_sharded(hnswb200_index* idx, const float* d_queries, 
 
 int hnswb200_get_info(hnswb200_index* idx, hnswb200_info* out);
 int hnswb200_get_stats(hnswb200_index* idx, hnswb200_stats* out);
-/* Pin / unpin a caller buffer (a Bigarray payload) so H2D/D2H copies are asynchronous DMA. */
+/* Pin / unpin a caller buffer (a Bigarray payload).  Copies from / to it are asynchronous DMA, and hnswb200_search
+ * does not copy it at all: the search kernel reads each query from it when a warp starts on that query and stores
+ * each result row into it when the query is done, so the PCIe traffic rides under the search.  Register whole
+ * buffers (the address range the call touches must lie inside one registration). */
 int hnswb200_host_register(const void* ptr, int64_t bytes);
 int hnswb200_host_unregister(const void* ptr);
 const char* hnswb200_last_error(void);

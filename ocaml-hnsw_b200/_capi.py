@@ -33,7 +33,8 @@ class Stats(C.Structure):
                 ("layer_nodes", C.c_int64 * 16), ("layer_min_degree", C.c_int32 * 16),
                 ("layer_max_degree", C.c_int32 * 16), ("layer_mean_degree", C.c_double * 16),
                 ("layer_isolated", C.c_int64 * 16), ("build_visited_overflows", C.c_uint64), ("search_tie_overflows", C.c_uint64),
-                ("search_tie_spills", C.c_uint64), ("build_dropped_incoming", C.c_uint64)]
+                ("search_tie_spills", C.c_uint64), ("build_dropped_incoming", C.c_uint64),
+                ("search_zero_copy", C.c_uint64)]
 
 
 class HnswB200Error(RuntimeError):
@@ -124,10 +125,22 @@ def as_mat(a, dim=None):
     return a
 
 
+_PINNED = {}          # address -> bytes of the buffers pinned through host_register (this process)
+
+
 def host_register(a):
-    """Pin a caller buffer (the payload of a Bigarray) so H2D / D2H copies are asynchronous DMA."""
+    """Pin a caller buffer (the payload of a Bigarray): copies from / to it are asynchronous DMA, and the search
+    reads queries from it / stores rows into it from inside the kernel, no copy (include/hnsw_b200.h)."""
     check(lib().hnswb200_host_register(ptr(a), a.nbytes))
+    _PINNED[a.ctypes.data] = a.nbytes
 
 
 def host_unregister(a):
     check(lib().hnswb200_host_unregister(ptr(a)))
+    _PINNED.pop(a.ctypes.data, None)
+
+
+def is_pinned(a):
+    """True when the bytes of `a` (a C-contiguous array or slice) lie inside a buffer pinned with host_register."""
+    lo = a.ctypes.data
+    return a.flags.c_contiguous and any(base <= lo and lo + a.nbytes <= base + n for base, n in _PINNED.items())

@@ -99,6 +99,8 @@ struct hnswb200_index {
   cudaEvent_t copy_event = nullptr;
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t param_host_chunks = 0;
+  int64_t param_host_zero_copy = 1;     // pinned caller buffers are read / written by the search kernel itself (search_host)
+  unsigned long long* h_evs = nullptr;  // pinned landing place of the event counters
   int64_t param_stage_rows = 0;         // 0 auto, -1 never stage, 4..32 rows in the ring
   int64_t param_stage_ahead = -1;       // rows beyond the ring prefetched to L2 (-1 auto, 0..31)
   int64_t param_gang = 0;               // warps per query: 0 auto (1 when the batch fills the GPU), 1, 2, 4
@@ -428,14 +430,27 @@ void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes, cudaStream
   }
 }
 
+// The device address of a pinned host buffer (registered with hnswb200_host_register / cudaHostRegister, or from
+// cudaMallocHost): under unified addressing such memory is mapped into every device.  Null for pageable memory.
+template <class T>
+T* device_view_of_pinned(T* p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, (const void*)p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return reinterpret_cast<T*>(a.devicePointer);
+}
+
 // Device-resident queries are dense [nq][dim]; when rows are padded (ld != dim) they are re-laid
-// into the index's own padded buffer first (one strided device-to-device copy).
+// into the index's own padded buffer first (one strided device-to-device copy).  A PINNED host buffer is
+// accepted in their place: the kernel then reads each query over PCIe when a warp starts on it.
 const float* padded_queries(hnswb200_index* x, const float* d_queries, int64_t nq, cudaStream_t s) {
+  if (const float* m = device_view_of_pinned(d_queries)) d_queries = m;
   if (x->ld == x->dim || nq == 0) return d_queries;
   x->d_q.reserve((size_t)nq * x->ld);
   CUDA_CHECK(cudaMemsetAsync(x->d_q.p, 0, (size_t)nq * x->ld * sizeof(float), s));
   CUDA_CHECK(cudaMemcpy2DAsync(x->d_q.p, (size_t)x->ld * sizeof(float), d_queries, (size_t)x->dim * sizeof(float),
-                               (size_t)x->dim * sizeof(float), (size_t)nq, cudaMemcpyDeviceToDevice, s));
+                               (size_t)x->dim * sizeof(float), (size_t)nq, cudaMemcpyDefault, s));
   return x->d_q.p;
 }
 
@@ -532,10 +547,14 @@ void search_device(hnswb200_index* x, const float* d_queries, int64_t nq, int k,
   }
 }
 
-// Ohnsw.knn_batch_bigarray with host buffers: H2D of the queries, search, D2H of the rows.
-// With "host_chunks" = 2..8, batches of >= 4096 queries are streamed (see below;
-// search_kernel_ms then includes the wait for the first piece).  Off by default: measured on
-// B200 it buys 1-2 % of the call (10k queries: 1.204 ms -> 1.185 ms), the copy is already short.
+// Ohnsw.knn_batch_bigarray with host buffers.  Pageable buffers: H2D of the queries, search, D2H of the rows.
+// PINNED buffers (the Bigarray payloads after hnswb200_host_register) are not copied at all: a warp reads its
+// 4*dim-byte query straight from host memory when it starts on it (one coalesced read over PCIe, ~2 us of a
+// ~100 us query) and stores its k-entry row straight into the caller's ids / dists, so the transfers ride
+// under the search instead of in front of and behind it (10k x 128 queries: 5.1 MB that cost 0.1 ms as a copy).
+// "host_zero_copy" = 0 restores the copies.  With "host_chunks" = 2..8, batches of >= 4096 queries are streamed
+// through device memory instead (see below; search_kernel_ms then includes the wait for the first piece) — off
+// by default: measured on B200 it buys 1-2 % of the call (10k queries: 1.204 ms -> 1.185 ms).
 constexpr int HOST_CHUNKS = 8;
 void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int ef, int mode, int32_t* ids, float* dists) {
   check_search_args(x, nq, k, ef, mode);
@@ -546,12 +565,17 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   if (pl.hash_slots == 0) pl.grid = std::max(1, std::min(pl.grid, x->pool_size / pl.warps));
   int C = x->param_host_chunks >= 2 ? (int)std::min<int64_t>(x->param_host_chunks, HOST_CHUNKS) : 1;
   if (nq < 4096) C = 1;
-  x->d_q.reserve((size_t)nq * x->ld);
-  x->d_ids.reserve((size_t)nq * k);
-  x->d_dists.reserve((size_t)nq * k);
+  const bool zc = C == 1 && x->param_host_zero_copy != 0;
+  const float* q_map = zc && x->ld == x->dim ? device_view_of_pinned(queries) : nullptr;   // padded rows are re-laid by the copy
+  int32_t* ids_map = zc ? device_view_of_pinned(ids) : nullptr;
+  float* d_map = zc ? device_view_of_pinned(dists) : nullptr;
+  if (!q_map) x->d_q.reserve((size_t)nq * x->ld);
+  if (ids && !ids_map) x->d_ids.reserve((size_t)nq * k);
+  if (!d_map) x->d_dists.reserve((size_t)nq * k);
   x->d_counters.reserve((size_t)nq * 3);
   x->d_next.reserve(8);
   x->d_events.reserve(4);
+  if (!x->h_evs) CUDA_CHECK(cudaMallocHost(&x->h_evs, 4 * sizeof(unsigned long long)));
   cudaStream_t s0 = x->stream;
   if (C > 1 && !x->aux_stream[0]) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&x->aux_stream[0], cudaStreamNonBlocking));
@@ -562,11 +586,12 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   // d_next[0] = work counter, d_next[1] = pieces of the batch copied so far
   CUDA_CHECK(cudaMemsetAsync(x->d_next.p, 0, 8 * sizeof(unsigned int), s0));
   CUDA_CHECK(cudaMemsetAsync(x->d_events.p, 0, 4 * sizeof(unsigned long long), s0));
-  unsigned long long evs[4];
+  int32_t* out_ids = ids ? (ids_map ? ids_map : x->d_ids.p) : nullptr;
+  float* out_d = d_map ? d_map : x->d_dists.p;
   if (C == 1) {
-    upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, s0);
+    if (!q_map) upload_rows(x->d_q.p, x->ld, queries, x->dim, nq, s0);
     CUDA_CHECK(cudaEventRecord(x->ev0, s0));
-    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0);
+    enqueue_search(x, pl, q_map ? q_map : x->d_q.p, nq, k, ef, out_ids, out_d, x->d_counters.p, x->d_next.p, s0);
   } else {
     // One kernel, started at once; the queries stream in behind it in C pieces on the copy stream,
     // each followed by a 4-byte "pieces ready" update the kernel's warps wait on (bounded) before
@@ -576,7 +601,7 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
     CUDA_CHECK(cudaEventRecord(x->aux_event[0], s0));
     CUDA_CHECK(cudaStreamWaitEvent(sc, x->aux_event[0], 0));          // counters are zero before any piece lands
     CUDA_CHECK(cudaEventRecord(x->ev0, s0));
-    enqueue_search(x, pl, x->d_q.p, nq, k, ef, x->d_ids.p, x->d_dists.p, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
+    enqueue_search(x, pl, x->d_q.p, nq, k, ef, out_ids, out_d, x->d_counters.p, x->d_next.p, s0, 0, nullptr, nullptr,
                    x->d_next.p + 1, step);
     for (int c = 0; c < C; c++) {
       const int64_t q0 = (int64_t)step * c, m = std::min<int64_t>(step, nq - q0);
@@ -586,18 +611,19 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
     }
   }
   CUDA_CHECK(cudaEventRecord(x->ev1, s0));
-  if (ids) CUDA_CHECK(cudaMemcpyAsync(ids, x->d_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
-  CUDA_CHECK(cudaMemcpyAsync(dists, x->d_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
-  CUDA_CHECK(cudaMemcpyAsync(evs, x->d_events.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
+  if (ids && !ids_map) CUDA_CHECK(cudaMemcpyAsync(ids, x->d_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
+  if (!d_map) CUDA_CHECK(cudaMemcpyAsync(dists, x->d_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s0));
+  CUDA_CHECK(cudaMemcpyAsync(x->h_evs, x->d_events.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
   x->search_pending = true;
   x->last_nq = nq;
   x->last_k = k;
   x->last_mode = mode;
   x->st.search_queries = (uint64_t)nq;
+  x->st.search_zero_copy = (q_map ? 1u : 0u) | (d_map && (!ids || ids_map) ? 2u : 0u);
   CUDA_CHECK(cudaStreamSynchronize(s0));
   if (C > 1) CUDA_CHECK(cudaStreamSynchronize(x->aux_stream[0]));
-  if (evs[2]) fail(HNSWB200_ECUDA, "search: the query copy did not arrive (streamed host buffers)");
-  finish_search(x, evs, mode);
+  if (x->h_evs[2]) fail(HNSWB200_ECUDA, "search: the query copy did not arrive (streamed host buffers)");
+  finish_search(x, x->h_evs, mode);
 }
 
 // ---- import / export ----------------------------------------------------------------------------------
@@ -740,6 +766,7 @@ int hnswb200_set_param(hnswb200_index* x, const char* name, int64_t value) {
     else if (s == "max_warps_per_sm") x->param_max_warps_per_sm = value;
     else if (s == "visited_mode") x->param_visited_mode = value;
     else if (s == "host_chunks") x->param_host_chunks = value;
+    else if (s == "host_zero_copy") x->param_host_zero_copy = value;
     else if (s == "stage_rows") x->param_stage_rows = value;
     else if (s == "stage_ahead") x->param_stage_ahead = value;
     else if (s == "hash_bits") x->param_hash_bits = value;
@@ -767,6 +794,7 @@ int hnswb200_destroy(hnswb200_index* x) {
     if (x->ev0) cudaEventDestroy(x->ev0);
     if (x->ev1) cudaEventDestroy(x->ev1);
     if (x->h_ready) cudaFreeHost(x->h_ready);
+    if (x->h_evs) cudaFreeHost(x->h_evs);
     if (x->copy_stream) { cudaStreamSynchronize(x->copy_stream); cudaStreamDestroy(x->copy_stream); }
     if (x->copy_event) cudaEventDestroy(x->copy_event);
     for (cudaStream_t a : x->aux_stream) if (a) cudaStreamDestroy(a);

@@ -227,7 +227,8 @@ class ShardedHgraph:
     def knn_batch_device(self, q_dev, *, k, ef=None, mode=capi.MODE_PARITY, nq=None):
         """Queries on this rank's GPU -> (ids int32 [nq][k] global, distances float32 [nq][k]) torch tensors on the
         GPU, on every rank.  `q_dev` is the whole batch (float32 [nq][dim], the same on every rank) or, with `nq`
-        given, only this rank's slice of it (`query_slice(nq)`).  Everything is enqueued on torch's current stream."""
+        given, only this rank's slice of it (`query_slice(nq)`; a torch tensor on the GPU or a pinned numpy array).
+        Everything is enqueued on torch's current stream."""
         import torch
         sliced = nq is not None
         nq = q_dev.shape[0] if nq is None else nq
@@ -249,7 +250,8 @@ class ShardedHgraph:
             if self.shard == 0:
                 nxt["arrive_t"].zero_()            # counters of the NEXT call; ordered before this call's barrier
             lo, hi = self.query_slice(nq)
-            q_ptr = q_dev.data_ptr() + (0 if sliced else lo * q_dev.shape[1] * 4)
+            q_base = q_dev.ctypes.data if isinstance(q_dev, np.ndarray) else q_dev.data_ptr()    # (a pinned host slice, see knn_batch_bigarray)
+            q_ptr = q_base + (0 if sliced else lo * q_dev.shape[1] * 4)
             if hi > lo:
                 capi.check(capi.lib().hnswb200_search_device_sharded(
                     self.local._h, q_ptr, hi - lo, k, k if ef is None else ef, mode, self.shard, self.S,
@@ -277,7 +279,10 @@ class ShardedHgraph:
         nq = batch.shape[0]
         if self._buffers(nq, k) and self._peer is not None:
             lo, hi = self.query_slice(nq)
-            q_dev = torch.from_numpy(batch[lo:hi]).to(dev, non_blocking=True)     # only the slice travels
+            if capi.is_pinned(batch[lo:hi]):
+                q_dev = batch[lo:hi]              # pinned: the kernel reads its slice of the queries from host memory, no copy
+            else:
+                q_dev = torch.from_numpy(batch[lo:hi]).to(dev, non_blocking=True)     # only the slice travels
             ids, d = self.knn_batch_device(q_dev, k=k, ef=ef, mode=mode, nq=nq)
         else:
             q_dev = torch.from_numpy(batch).to(dev, non_blocking=True)

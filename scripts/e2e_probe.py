@@ -9,10 +9,11 @@ X = H.sift_like(n, 128, seed=1234); Q = np.ascontiguousarray(H.sift_like(10000, 
 h = Ohnsw.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=16, num_nodes_search_construction=200, levels=draw_levels(n, 16, 7))
 out = (np.empty((10000, 10), np.int32), np.empty((10000, 10), np.float32))
 for b in (Q,) + out: capi.host_register(b)
-for C in (1, 2, 4, 8, 1, 4):
+for C, zc in ((1, 1), (1, 0), (4, 0), (8, 0), (1, 1), (1, 0)):
     h.set_param("host_chunks", C)
+    h.set_param("host_zero_copy", zc)
     for _ in range(3): Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=41, out=out)
     t = time.perf_counter()
     for _ in range(20): Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=41, out=out)
     dt = (time.perf_counter() - t) / 20
-    print(f"host_chunks={C}: {dt*1e3:.3f} ms per call, {10000/dt/1e6:.2f} M queries/s", flush=True)
+    print(f"host_chunks={C} zero_copy={zc} (path bits {h.stats().search_zero_copy}, kernel {h.stats().search_kernel_ms:.3f} ms): {dt*1e3:.3f} ms per call, {10000/dt/1e6:.2f} M queries/s", flush=True)

@@ -94,3 +94,17 @@ def test_fbin_roundtrip_and_dot(tmp_path):
     H.write_graph(p, g, dim=5, M=2, vectors=a[:3])
     g2, meta, vec = H.read_graph(p)
     assert g2.entry == 1 and meta["dim"] == 5 and np.array_equal(vec, a[:3]) and np.array_equal(g2.nbrs[0], g.nbrs[0])
+
+
+def test_pinned_buffer_registry():
+    """capi.is_pinned: a slice is pinned when its bytes lie inside a buffer registered with host_register (what lets
+    the sharded host mirror hand a query slice to the kernel without a copy)."""
+    a = np.zeros((100, 8), np.float32)
+    capi._PINNED[a.ctypes.data] = a.nbytes            # what host_register records (no GPU here)
+    try:
+        assert capi.is_pinned(a) and capi.is_pinned(a[10:20]) and capi.is_pinned(a[99:])
+        assert not capi.is_pinned(a[:, :4])            # not contiguous
+        assert not capi.is_pinned(np.zeros((4, 8), np.float32))
+    finally:
+        capi._PINNED.pop(a.ctypes.data)
+    assert not capi.is_pinned(a)

@@ -327,6 +327,45 @@ def test_wider_row_stride_is_invisible(dim, rf, metric):
         assert np.array_equal(g.offsets[l], go.offsets[l]) and np.array_equal(g.nbrs[l], go.nbrs[l])
 
 
+@pytest.mark.parametrize("dim", [64, 6])
+def test_pinned_host_buffers_are_read_and_written_in_place(dim):
+    """hnswb200_search with PINNED buffers (hnswb200_host_register): the kernel reads the queries from the caller's
+    buffer and stores the rows into it, no copy — same ids, distances and counters as with pageable buffers (and as
+    the oracle), `search_zero_copy` says which path ran; rows the index pads (dim = 6) still take the copy."""
+    X, Q = uniform(1500, dim, 81), np.ascontiguousarray(uniform(200, dim, 82))
+    o = _oracle_index(X, 8, 50)
+    h = _gpu_from(o, X, 8, 50)
+    ids_o, d_o, cnt_o = o.search(Q, 10, 40, counters=True)
+    ids_p, d_p = Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=40)                    # pageable
+    assert h.stats().search_zero_copy == 0
+    out = (np.full((200, 10), -7, np.int32), np.full((200, 10), -7.0, np.float32))
+    for b in (Q,) + out:
+        capi.host_register(b)
+    try:
+        Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=40, out=out)
+        assert h.stats().search_zero_copy == (3 if dim % 4 == 0 else 2)
+        assert_same_results(out[0], out[1], ids_o, d_o)
+        assert np.array_equal(out[0], ids_p) and np.array_equal(out[1].view(np.uint32), d_p.view(np.uint32))
+        assert np.array_equal(h.last_search_counters(200).astype(np.uint64), cnt_o)
+        Q[:] = Q[::-1].copy()                                                   # new contents, same pinned buffer
+        Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=40, out=out)
+        assert np.array_equal(out[0], ids_p[::-1])
+        # the device-pointer entry points take a pinned host buffer for the queries too (read in place by the kernel)
+        import torch
+        ids_t = torch.empty((200, 10), dtype=torch.int32, device="cuda")
+        d_t = torch.empty((200, 10), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        h.search_device(Q.ctypes.data, 200, 10, 40, ids_t.data_ptr(), d_t.data_ptr())
+        assert np.array_equal(ids_t.cpu().numpy(), ids_p[::-1])
+        h.set_param("host_zero_copy", 0)
+        out[0][:] = -7
+        Ohnsw.knn_batch_bigarray(h, Q, k=10, ef=40, out=out)
+        assert h.stats().search_zero_copy == 0 and np.array_equal(out[0], ids_p[::-1])
+    finally:
+        for b in (Q,) + out:
+            capi.host_unregister(b)
+
+
 def test_hnsw_ba_acceptance_rule_on_tie_heavy_data():
     """HNSW_BA flavour: candidates that TIE with the beam's maximum are accepted (lib/hnsw.ml:494-506).
     Integer data makes ties the common case; ids, distances and counters must equal the oracle run
