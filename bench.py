@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--ref-n", type=int, default=400_000,
                     help="--impl reference: rows the sequential CPU build covers (a prefix of the dataset; 400k rows build in "
                          "about 4 minutes on one host core, the full 1M in about a quarter of an hour)")
+    ap.add_argument("--ref-build-seconds", type=float, default=450.0,
+                    help="--impl reference: the sequential CPU build stops taking rows after this long (checked every 20k rows), so a "
+                         "slow host shortens the indexed prefix instead of running into the driver's limit; `index_rows` says how far it got")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--metric", default="l2", choices=["l2", "angular"],
                     help="angular = SURVEY.md config C3 (GloVe shape): unit-norm Gaussian-mixture vectors, distance 1 - a.b")
@@ -233,8 +236,17 @@ def run_reference(a):
     om = O.METRIC_L2 if a.metric == "l2" else O.METRIC_ANGULAR
     lv = draw_levels(n, a.M, 7)
     t0 = time.time()
-    o = O.VecOracle(a.dim, om).build(X, a.M, a.efc, lv)
+    o = O.VecOracle(a.dim, om)
+    done, chunk = 0, 20_000                        # sequential inserts, continued call after call (Ohnsw.insert, lib/ohnsw.ml:766)
+    while done < n:
+        m = min(chunk, n - done)
+        o.build(X[done:done + m], a.M, a.efc, lv[done:done + m])
+        done += m
+        if time.time() - t0 > a.ref_build_seconds:
+            break
     build_s = time.time() - t0
+    if done < n:                                   # out of time: the index is the prefix inserted so far
+        n, X = done, np.ascontiguousarray(X[:done])
     gt_n = min(a.nq, 2000)
     gt, _ = O.bruteforce(X, Q[:gt_n], a.k, om, nthreads=threads)
     def recall_at(ef):

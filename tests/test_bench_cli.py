@@ -26,6 +26,16 @@ def test_reference_arm_prints_one_json_line():
     assert j["config"]["recall_at_10"] >= 0.95 and j["steps"] == 2 and j["warmup"] == 1
 
 
+def test_reference_arm_build_is_time_bounded():
+    """--ref-build-seconds: the sequential CPU build stops taking rows when its time is up (checked per 20k rows) and the line
+    says how many rows the index holds."""
+    r = _run(["--impl", "reference", "--n", "50000", "--ref-n", "50000", "--nq", "100", "--efc", "20", "--M", "6", "--steps", "1",
+              "--warmup", "1", "--ref-build-seconds", "0"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert j["config"]["index_rows"] == 20000 and j["same_config"] is False
+
+
 def test_reference_arm_other_ranks_do_nothing():
     r = _run(["--impl", "reference", "--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
