@@ -270,7 +270,9 @@ int hnswb200_sharded_set_flavour(hnswb200_sharded* s, int flavour);
  * `levels` (int32[n], may be NULL) as in hnswb200_build. */
 int hnswb200_sharded_build(hnswb200_sharded* s, const float* data, int64_t n, const int32_t* levels);
 /* Ohnsw.knn_batch_bigarray (lib/ohnsw.ml:877-897): host buffers, global ids, rows ascending by
- * (distance, id) over all shards, -1 / NaN padded. */
+ * (distance, id) over all shards, -1 / NaN padded.  Pinned buffers (hnswb200_host_register) are not copied:
+ * every shard's kernel reads the batch from host memory over its own PCIe link, and the warp that merges a
+ * query stores its row into the caller's arrays. */
 int hnswb200_sharded_search(hnswb200_sharded* s, const float* queries, int64_t nq, int k, int ef, int mode,
                             int32_t* ids, float* dists);
 /* Same with every buffer on the FIRST shard's device (queries dense [nq][dim]); `stream` as in

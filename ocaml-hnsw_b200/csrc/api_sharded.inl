@@ -124,7 +124,11 @@ void sharded_enqueue(hnswb200_sharded* s, const float* h_queries, const float* d
   s->calls++;
   // queries on the home device, padded to the row stride
   const float* q_home;
-  if (h_queries) {
+  // a pinned host batch is read in place by every shard's kernel (each GPU over its own PCIe link): no copy at all
+  const float* q_pinned = h_queries && s->ld == s->dim && s->param_query_path != 1 && s->shard[0]->param_host_zero_copy != 0
+                              ? device_view_of_pinned(h_queries) : nullptr;
+  if (q_pinned) q_home = q_pinned;
+  else if (h_queries) {
     s->q_home.reserve((size_t)nq * s->ld);
     upload_rows(s->q_home.p, s->ld, h_queries, s->dim, nq, s->hs);
     q_home = s->q_home.p;
@@ -146,7 +150,7 @@ void sharded_enqueue(hnswb200_sharded* s, const float* h_queries, const float* d
     cudaStream_t st = s->stream[i];
     const float* q = q_home;
     CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_q, 0));
-    if (s->device[i] != s->home) {
+    if (s->device[i] != s->home && !q_pinned) {
       const size_t want = (size_t)nq * s->ld;
       if (want > s->q_local_n[i]) {
         if (s->q_local[i]) cudaFree(s->q_local[i]);
@@ -307,10 +311,15 @@ int hnswb200_sharded_search(hnswb200_sharded* s, const float* queries, int64_t n
     if (!queries || !dists) fail(HNSWB200_EINVAL, "search: queries/dists is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     CUDA_CHECK(cudaSetDevice(s->home));
-    s->out_ids.reserve((size_t)nq * k); s->out_dists.reserve((size_t)nq * k);
-    sharded_enqueue(s, queries, nullptr, nq, k, ef, mode, s->out_ids.p, s->out_dists.p);
-    if (ids) CUDA_CHECK(cudaMemcpyAsync(ids, s->out_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s->hs));
-    CUDA_CHECK(cudaMemcpyAsync(dists, s->out_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s->hs));
+    // pinned result buffers take the merged rows straight from the warp that merges them (whichever GPU it runs on)
+    const bool zc = s->shard[0]->param_host_zero_copy != 0;
+    int32_t* ids_map = zc ? device_view_of_pinned(ids) : nullptr;
+    float* d_map = zc ? device_view_of_pinned(dists) : nullptr;
+    if (!ids_map) s->out_ids.reserve((size_t)nq * k);
+    if (!d_map) s->out_dists.reserve((size_t)nq * k);
+    sharded_enqueue(s, queries, nullptr, nq, k, ef, mode, ids_map ? ids_map : s->out_ids.p, d_map ? d_map : s->out_dists.p);
+    if (ids && !ids_map) CUDA_CHECK(cudaMemcpyAsync(ids, s->out_ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s->hs));
+    if (!d_map) CUDA_CHECK(cudaMemcpyAsync(dists, s->out_dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s->hs));
     CUDA_CHECK(cudaStreamSynchronize(s->hs));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1) == cudaSuccess) s->last_search_ms = ms; else cudaGetLastError();

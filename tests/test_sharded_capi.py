@@ -70,6 +70,28 @@ def test_sharded_search_is_the_exact_merge(n_shards, n, dim, M):
     assert H.Recall.ids(gt, ids) > 0.9
 
 
+def test_sharded_search_with_pinned_host_buffers():
+    """hnswb200_sharded_search with pinned buffers: every shard's kernel reads the batch from host memory and the warp that
+    merges a query stores its row into the caller's arrays — the same rows as with pageable buffers, call after call."""
+    n, dim = 5000, 64
+    X, lv = uniform(n, dim, 41), draw_levels(n, 8)
+    m = MultiGpuHgraph.build_batch_bigarray(Ohnsw.distance_l2, X, num_connections=8, num_nodes_search_construction=50,
+                                            devices=[0, 0, 0], levels=lv)
+    Q = np.ascontiguousarray(uniform(300, dim, 42))
+    out = (np.full((300, 10), -7, np.int32), np.full((300, 10), -7.0, np.float32))
+    want = [m.knn_batch_bigarray(Q[::s].copy() if s == 1 else Q[::-1].copy(), k=10, ef=40) for s in (1, -1)]
+    for b in (Q,) + out:
+        capi.host_register(b)
+    try:
+        for rep in range(2):
+            m.knn_batch_bigarray(Q, k=10, ef=40, out=out)
+            assert np.array_equal(out[0], want[rep][0]) and np.array_equal(out[1].view(np.uint32), want[rep][1].view(np.uint32))
+            Q[:] = Q[::-1].copy()                          # new contents in the same pinned buffer for the next call
+    finally:
+        for b in (Q,) + out:
+            capi.host_unregister(b)
+
+
 def test_sharded_device_buffers_and_streams():
     """hnswb200_sharded_search_device: queries and results in device memory, on a caller's stream, batch contents
     changing from call to call (the calls are ordered with the caller's copies)."""
