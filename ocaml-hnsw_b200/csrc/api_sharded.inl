@@ -126,7 +126,7 @@ void sharded_enqueue(hnswb200_sharded* s, const float* h_queries, const float* d
   const float* q_home;
   // a pinned host batch is read in place by every shard's kernel (each GPU over its own PCIe link): no copy at all
   const float* q_pinned = h_queries && s->ld == s->dim && s->param_query_path != 1 && s->shard[0]->param_host_zero_copy != 0
-                              ? device_view_of_pinned(h_queries) : nullptr;
+                              ? device_view_of_pinned(h_queries, (size_t)nq * s->dim) : nullptr;
   if (q_pinned) q_home = q_pinned;
   else if (h_queries) {
     s->q_home.reserve((size_t)nq * s->ld);
@@ -313,8 +313,8 @@ int hnswb200_sharded_search(hnswb200_sharded* s, const float* queries, int64_t n
     CUDA_CHECK(cudaSetDevice(s->home));
     // pinned result buffers take the merged rows straight from the warp that merges them (whichever GPU it runs on)
     const bool zc = s->shard[0]->param_host_zero_copy != 0;
-    int32_t* ids_map = zc ? device_view_of_pinned(ids) : nullptr;
-    float* d_map = zc ? device_view_of_pinned(dists) : nullptr;
+    int32_t* ids_map = zc ? device_view_of_pinned(ids, (size_t)nq * k) : nullptr;
+    float* d_map = zc ? device_view_of_pinned(dists, (size_t)nq * k) : nullptr;
     if (!ids_map) s->out_ids.reserve((size_t)nq * k);
     if (!d_map) s->out_dists.reserve((size_t)nq * k);
     sharded_enqueue(s, queries, nullptr, nq, k, ef, mode, ids_map ? ids_map : s->out_ids.p, d_map ? d_map : s->out_dists.p);

@@ -430,14 +430,19 @@ void ensure_pool(hnswb200_index* x, int total_warps, int64_t n_nodes, cudaStream
   }
 }
 
-// The device address of a pinned host buffer (registered with hnswb200_host_register / cudaHostRegister, or from
-// cudaMallocHost): under unified addressing such memory is mapped into every device.  Null for pageable memory.
+// The device address of a pinned host buffer of `count` elements (registered with hnswb200_host_register /
+// cudaHostRegister, or from cudaMallocHost): under unified addressing such memory is mapped into every device.
+// Null for pageable memory, and for a buffer whose last byte is not pinned and mapped in line with its first
+// (a registration that covers only part of it): those take the copies.
 template <class T>
-T* device_view_of_pinned(T* p) {
-  if (!p) return nullptr;
-  cudaPointerAttributes a;
+T* device_view_of_pinned(T* p, size_t count) {
+  if (!p || count == 0) return nullptr;
+  cudaPointerAttributes a, b;
   if (cudaPointerGetAttributes(&a, (const void*)p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  const size_t last = count * sizeof(T) - 1;
+  if (cudaPointerGetAttributes(&b, (const void*)((const char*)p + last)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (b.type != cudaMemoryTypeHost || (const char*)b.devicePointer != (const char*)a.devicePointer + last) return nullptr;
   return reinterpret_cast<T*>(a.devicePointer);
 }
 
@@ -445,7 +450,7 @@ T* device_view_of_pinned(T* p) {
 // into the index's own padded buffer first (one strided device-to-device copy).  A PINNED host buffer is
 // accepted in their place: the kernel then reads each query over PCIe when a warp starts on it.
 const float* padded_queries(hnswb200_index* x, const float* d_queries, int64_t nq, cudaStream_t s) {
-  if (const float* m = device_view_of_pinned(d_queries)) d_queries = m;
+  if (const float* m = device_view_of_pinned(d_queries, (size_t)nq * x->dim)) d_queries = m;
   if (x->ld == x->dim || nq == 0) return d_queries;
   x->d_q.reserve((size_t)nq * x->ld);
   CUDA_CHECK(cudaMemsetAsync(x->d_q.p, 0, (size_t)nq * x->ld * sizeof(float), s));
@@ -566,9 +571,9 @@ void search_host(hnswb200_index* x, const float* queries, int64_t nq, int k, int
   int C = x->param_host_chunks >= 2 ? (int)std::min<int64_t>(x->param_host_chunks, HOST_CHUNKS) : 1;
   if (nq < 4096) C = 1;
   const bool zc = C == 1 && x->param_host_zero_copy != 0;
-  const float* q_map = zc && x->ld == x->dim ? device_view_of_pinned(queries) : nullptr;   // padded rows are re-laid by the copy
-  int32_t* ids_map = zc ? device_view_of_pinned(ids) : nullptr;
-  float* d_map = zc ? device_view_of_pinned(dists) : nullptr;
+  const float* q_map = zc && x->ld == x->dim ? device_view_of_pinned(queries, (size_t)nq * x->dim) : nullptr;   // padded rows are re-laid by the copy
+  int32_t* ids_map = zc ? device_view_of_pinned(ids, (size_t)nq * k) : nullptr;
+  float* d_map = zc ? device_view_of_pinned(dists, (size_t)nq * k) : nullptr;
   if (!q_map) x->d_q.reserve((size_t)nq * x->ld);
   if (ids && !ids_map) x->d_ids.reserve((size_t)nq * k);
   if (!d_map) x->d_dists.reserve((size_t)nq * k);
