@@ -65,6 +65,10 @@ def parse():
     ap.add_argument("--metric", default="l2", choices=["l2", "angular"],
                     help="angular = SURVEY.md config C3 (GloVe shape): unit-norm Gaussian-mixture vectors, distance 1 - a.b")
     ap.add_argument("--latent", type=int, default=16, help="latent dimension of the SIFT-like generator")
+    ap.add_argument("--generator", default="sift-like", choices=["sift-like", "uniform"],
+                    help="L2 data: SURVEY.md section 8d generator (b), the headline, or (a) iid uniform [-1, 1) (Lacaml.S.Mat.random, "
+                         "benchmark/dataset.ml:48) — (a) does not reach recall 0.95 at any ef of the sweep, the line then reports the "
+                         "largest ef and the recall it reached")
     ap.add_argument("--replicas", type=int, default=0,
                     help="N > 1: the GPUs form S row shards x R replicas (S * R = N).  0 = automatic: R = N when one GPU holds the "
                          "whole index (every config but c5), so each GPU answers 1/N of the queries on the full graph; R = 1 = "
@@ -95,6 +99,8 @@ CONFIGS = {
 def workload_name(a):
     if a.metric == "angular":
         return f"unit-norm gaussian-mixture {a.n}x{a.dim} fp32 angular, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
+    if getattr(a, "generator", "sift-like") == "uniform":
+        return f"uniform[-1,1) {a.n}x{a.dim} fp32 L2, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
     lat = "" if a.latent == 16 else f" ({a.latent}-d latent)"
     return f"sift-like{lat} {a.n}x{a.dim} fp32 L2, {a.nq} queries, M={a.M}, efConstruction={a.efc}, k={a.k}"
 
@@ -103,6 +109,8 @@ def make_data(a, n, seed):
     """The synthetic generators of SURVEY.md section 8d: (b) SIFT-like for L2, a unit-norm Gaussian
     mixture (256 centres, sigma 0.35) for the angular config."""
     import ocaml_hnsw_b200.dataset as D
+    if a.metric == "l2" and getattr(a, "generator", "sift-like") == "uniform":
+        return np.random.default_rng(seed).random((n, a.dim), dtype=np.float32) * 2 - 1
     if a.metric == "l2":
         return D.sift_like(n, a.dim, latent=a.latent, seed=seed)
     centres = np.random.default_rng(99).standard_normal((256, a.dim)).astype(np.float32)
