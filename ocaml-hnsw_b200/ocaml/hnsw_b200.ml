@@ -23,6 +23,9 @@ external search_ : index -> Lacaml.S.mat -> int -> int -> i32mat -> Lacaml.S.mat
 external info : index -> int * int * int = "hb_info"
 external params : index -> int * int = "hb_params"            (* num_connections, num_nodes_search_construction *)
 external bruteforce_ : Lacaml.S.mat -> Lacaml.S.mat -> int -> Lacaml.S.mat -> unit = "hb_bruteforce"
+(* hnswb200_host_register on a Bigarray payload (off-heap, never moved by the GC).  knn_batch_bigarray on pinned
+   query / result Bigarrays copies nothing: the search kernel reads each query from the Bigarray and stores each result
+   row into it over PCIe while it runs (include/hnsw_b200.h). *)
 external pin : ('a, 'b, 'c) Bigarray.Genarray.t -> unit = "hb_pin"
 external unpin : ('a, 'b, 'c) Bigarray.Genarray.t -> unit = "hb_unpin"
 
